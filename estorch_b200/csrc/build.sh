@@ -1,0 +1,20 @@
+#!/bin/bash
+# Build libestk.so in-tree for sm_100a (B200).  nvcc cross-compiles without a GPU.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+OUT="$ROOT/estorch_b200/lib"
+mkdir -p "$OUT"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -I"$ROOT/include"
+       -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --cudart static)
+OBJS=()
+for src in "$HERE"/*.cu; do
+  obj="$OUT/$(basename "${src%.cu}").o"
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/estk_common.cuh" -nt "$obj" || "$ROOT/include/estk.h" -nt "$obj" ]]; then
+    "$NVCC" "${FLAGS[@]}" ${ESTK_PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj"
+  fi
+  OBJS+=("$obj")
+done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared --cudart static -o "$OUT/libestk.so" "${OBJS[@]}"
+echo "built $OUT/libestk.so"

@@ -1,0 +1,450 @@
+// estk_rank_grad.cu -- kernel 2 of the ES generation: centred-rank transform of
+// the P returns, the weighted noise reduction g = (1/P) sum_j w_j T[off_j:off_j+n]
+// and the negate/clamp/Adam update, as ONE cooperative persistent launch.
+//
+// Replaces (reference file:line, /root/reference/estorch/estorch.py):
+//   _compute_ranks :22-26, _center_function :15-20, rank_transformation :28-39
+//   ES._calculate_grad :174-179 (+ NS :419-425, NSR :542-549, NSRA :640-648)
+//   grad scatter + clamp :236-244, optimizer.step() :245 (torch Adam)
+//
+// Roofline: HBM-bound by the noise stream.  Algorithmic bytes per launch =
+// 4*n*pairs_local (each pair's unit-normal row once; the reference's torch.mm
+// reads both [eps; -eps] halves, 2x this) + 28*n (theta/m/v read+write, g) + 8*P.
+//
+// Decomposition: grid = CS column-splits x PS pair-splits, all CTAs co-resident.
+//   phase A  every warp ranks members (all-pairs count, O(P^2) compares total;
+//            bit-exact integer ranks; stable-by-index on ties), centres in
+//            fp64 -> fp32 and blends reward/novelty rows          -> grid.sync
+//   phase B  CTA (cs, ps) owns float4 columns [c0,c1) and sorted pair slots
+//            [s0,s1): 128-bit read-only loads, fp32 FMA into registers, 8
+//            independent loads in flight per thread.  With PS == 1 every CTA
+//            walks all pairs in the same (offset-sorted) order, so rows that
+//            overlap in the table are served from L2 instead of HBM.
+//   phase C  PS == 1: epilogue straight from registers.  PS > 1: partial sums
+//            to the workspace -> grid.sync -> fixed-order sum -> epilogue
+//            (deterministic; no atomics anywhere).
+#include "estk_common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPairTile = 256;  // pair weights / offsets staged per shared-memory refill
+
+struct RankGradParams {
+  const float* returns;
+  const float* novelty;  // nullable
+  float w_rew, w_nov;
+  int P, pairs;          // global population / pair count
+  int pair_begin, pairs_local;
+  const float* table;
+  const int64_t* offsets;  // [pairs_local]
+  const int32_t* order;    // [pairs_local] nullable
+  int64_t n, n4;
+  int CS, PS;
+  float* cvals;    // [P] workspace
+  float* partial;  // [PS * n4 * 4] workspace (PS > 1)
+  int32_t* ranks_out;
+  int32_t* ranks2_out;
+  // epilogue
+  int fused_adam;       // 1: Adam in place; 0: raw sum -> grad_sum_out
+  float* grad_sum_out;  // [n] (fused_adam == 0)
+  float* grad_out;      // [n] nullable: g (fused) -- the reference's un-negated estimate
+  float* theta;
+  float* m;
+  float* v;
+  estk_state* state;
+  estk_adam_desc adam;
+};
+
+struct AdamScalars {
+  float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step, wd, clamp, inv_div;
+};
+
+__device__ __forceinline__ float centre(int rank, int P) {
+  // estorch.py:17-19 in float64, cast to fp32 at :176
+  return (float)((double)rank / (double)(P - 1) - 0.5);
+}
+
+// torch.optim.Adam single-tensor update on one element (torch/optim/adam.py:
+// lerp_ :457, mul_/addcmul_ :476, sqrt/div/add_ :529-545, addcdiv_ :546), with
+// IEEE-rounded individual operations (no FMA contraction) like the CPU kernels.
+__device__ __forceinline__ void adam_elem(float sum, const AdamScalars& a, float& th, float& m,
+                                          float& v, float* g_out) {
+  const float g = __fdiv_rn(sum, a.inv_div);  // inv_div holds (float)P
+  if (g_out) *g_out = g;
+  float gp = -g;                               // estorch.py:239
+  if (a.clamp > 0.f) gp = fminf(fmaxf(gp, -a.clamp), a.clamp);  // :243
+  if (a.wd != 0.f) gp = __fadd_rn(gp, __fmul_rn(a.wd, th));
+  m = __fadd_rn(m, __fmul_rn(__fsub_rn(gp, m), a.one_minus_b1));
+  v = __fmul_rn(v, a.b2);
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(a.one_minus_b2, gp), gp));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.bc2_sqrt), a.eps);
+  th = __fadd_rn(th, __fdiv_rn(__fmul_rn(a.neg_step, m), denom));
+}
+
+__device__ __forceinline__ void epilogue(const RankGradParams& p, const AdamScalars& a,
+                                         int64_t col4, float4 s) {
+  const int64_t k = col4 * 4;
+  const bool full = (k + 3 < p.n);
+  if (!p.fused_adam) {
+    if (full) {
+      reinterpret_cast<float4*>(p.grad_sum_out)[col4] = s;
+    } else {
+      const float sv[4] = {s.x, s.y, s.z, s.w};
+      for (int e = 0; e < 4 && k + e < p.n; ++e) p.grad_sum_out[k + e] = sv[e];
+    }
+    return;
+  }
+  float sv[4] = {s.x, s.y, s.z, s.w};
+  float th[4], mm[4], vv[4], gg[4];
+  if (full) {
+    const float4 t4 = reinterpret_cast<const float4*>(p.theta)[col4];
+    const float4 m4 = reinterpret_cast<const float4*>(p.m)[col4];
+    const float4 v4 = reinterpret_cast<const float4*>(p.v)[col4];
+    th[0] = t4.x; th[1] = t4.y; th[2] = t4.z; th[3] = t4.w;
+    mm[0] = m4.x; mm[1] = m4.y; mm[2] = m4.z; mm[3] = m4.w;
+    vv[0] = v4.x; vv[1] = v4.y; vv[2] = v4.z; vv[3] = v4.w;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) adam_elem(sv[e], a, th[e], mm[e], vv[e], &gg[e]);
+    reinterpret_cast<float4*>(p.theta)[col4] = make_float4(th[0], th[1], th[2], th[3]);
+    reinterpret_cast<float4*>(p.m)[col4] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(p.v)[col4] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (p.grad_out) reinterpret_cast<float4*>(p.grad_out)[col4] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+  } else {
+    for (int e = 0; e < 4 && k + e < p.n; ++e) {
+      float t = p.theta[k + e], m_ = p.m[k + e], v_ = p.v[k + e], g_;
+      adam_elem(sv[e], a, t, m_, v_, &g_);
+      p.theta[k + e] = t; p.m[k + e] = m_; p.v[k + e] = v_;
+      if (p.grad_out) p.grad_out[k + e] = g_;
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kThreads) rank_grad_kernel(const RankGradParams p) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  __shared__ float s_w[kPairTile];
+  __shared__ uint32_t s_off4[kPairTile];
+  __shared__ AdamScalars s_adam;
+
+  // ---- Adam scalars (read adam_step BEFORE the first grid.sync; block 0
+  //      publishes the increment after the last one, so there is no race)
+  int64_t adam_t = 0;
+  if (p.fused_adam) adam_t = p.state->adam_step + 1;
+  if (tid == 0) {
+    AdamScalars a;
+    a.inv_div = (float)p.P;
+    a.clamp = p.adam.clamp;
+    a.one_minus_b1 = (float)(1.0 - p.adam.beta1);
+    a.b2 = (float)p.adam.beta2;
+    a.one_minus_b2 = (float)(1.0 - p.adam.beta2);
+    a.eps = (float)p.adam.eps;
+    a.wd = (float)p.adam.weight_decay;
+    if (p.fused_adam) {
+      const double bc1 = 1.0 - pow(p.adam.beta1, (double)adam_t);
+      const double bc2 = 1.0 - pow(p.adam.beta2, (double)adam_t);
+      a.bc2_sqrt = (float)sqrt(bc2);
+      a.neg_step = (float)(-(p.adam.lr / bc1));
+    } else {
+      a.bc2_sqrt = 1.f; a.neg_step = 0.f;
+    }
+    s_adam = a;
+  }
+
+  // ---- phase A: ranks.  rank_i = #{j: r_j < r_i} + #{j < i: r_j == r_i}
+  {
+    const int warps = kThreads >> 5;
+    const int gwarp = blockIdx.x * warps + (tid >> 5);
+    const int nwarps = gridDim.x * warps;
+    for (int i = gwarp; i < p.P; i += nwarps) {
+      const float ri = __ldg(p.returns + i);
+      int cnt = 0;
+      for (int j = lane; j < p.P; j += 32) {
+        const float rj = __ldg(p.returns + j);
+        cnt += (rj < ri) || (rj == ri && j < i);
+      }
+      cnt = warp_sum_i(cnt);
+      int cnt2 = 0;
+      if (p.novelty) {
+        const float qi = __ldg(p.novelty + i);
+        for (int j = lane; j < p.P; j += 32) {
+          const float qj = __ldg(p.novelty + j);
+          cnt2 += (qj < qi) || (qj == qi && j < i);
+        }
+        cnt2 = warp_sum_i(cnt2);
+      }
+      if (lane == 0) {
+        float c = centre(cnt, p.P);
+        if (p.novelty) {
+          // estorch.py:645-646  w*c(reward) + (1-w)*c(novelty), fp32, two roundings + add
+          c = __fadd_rn(__fmul_rn(p.w_rew, c), __fmul_rn(p.w_nov, centre(cnt2, p.P)));
+          if (p.ranks2_out) p.ranks2_out[i] = cnt2;
+        }
+        p.cvals[i] = c;
+        if (p.ranks_out) p.ranks_out[i] = cnt;
+      }
+    }
+  }
+  __threadfence();
+  grid.sync();
+
+  // ---- phase B: weighted noise reduction
+  const int cs = blockIdx.x % p.CS;
+  const int ps = blockIdx.x / p.CS;
+  const int64_t c0 = (int64_t)cs * p.n4 / p.CS;
+  const int64_t c1 = (int64_t)(cs + 1) * p.n4 / p.CS;
+  const int s0 = (int)((int64_t)ps * p.pairs_local / p.PS);
+  const int s1 = (int)((int64_t)(ps + 1) * p.pairs_local / p.PS);
+  const float4* tab4 = reinterpret_cast<const float4*>(p.table);
+  const AdamScalars adam = s_adam;  // valid: written before the __syncthreads in grid.sync
+
+  for (int64_t cbase = c0; cbase < c1; cbase += (int64_t)kThreads * NC) {
+    int64_t col[NC];
+    bool act[NC];
+    float4 acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      col[c] = cbase + (int64_t)c * kThreads + tid;
+      act[c] = col[c] < c1;
+      acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int sbase = s0; sbase < s1; sbase += kPairTile) {
+      const int cnt = min(kPairTile, s1 - sbase);
+      __syncthreads();
+      for (int t = tid; t < cnt; t += kThreads) {
+        const int jl = p.order ? p.order[sbase + t] : (sbase + t);
+        const int jg = p.pair_begin + jl;
+        // (c_j) * eps_j + (c_{j+pairs}) * (-eps_j)  ==  (c_j - c_{j+pairs}) * eps_j
+        s_w[t] = __fsub_rn(__ldcg(p.cvals + jg), __ldcg(p.cvals + jg + p.pairs));
+        s_off4[t] = (uint32_t)(p.offsets[jl] >> 2);
+      }
+      __syncthreads();
+      constexpr int U = 8 / NC;  // 8 independent 16-byte loads in flight per thread
+      int jj = 0;
+      for (; jj + U <= cnt; jj += U) {
+        float4 t[U][NC];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            if (act[c]) t[u][c] = ld_noise4(tab4 + (size_t)s_off4[jj + u] + col[c]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float w = s_w[jj + u];
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            if (act[c]) {
+              acc[c].x = fmaf(w, t[u][c].x, acc[c].x);
+              acc[c].y = fmaf(w, t[u][c].y, acc[c].y);
+              acc[c].z = fmaf(w, t[u][c].z, acc[c].z);
+              acc[c].w = fmaf(w, t[u][c].w, acc[c].w);
+            }
+        }
+      }
+      for (; jj < cnt; ++jj) {
+        const float w = s_w[jj];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (act[c]) {
+            const float4 t = ld_noise4(tab4 + (size_t)s_off4[jj] + col[c]);
+            acc[c].x = fmaf(w, t.x, acc[c].x);
+            acc[c].y = fmaf(w, t.y, acc[c].y);
+            acc[c].z = fmaf(w, t.z, acc[c].z);
+            acc[c].w = fmaf(w, t.w, acc[c].w);
+          }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (!act[c]) continue;
+      if (p.PS == 1) {
+        epilogue(p, adam, col[c], acc[c]);
+      } else {
+        reinterpret_cast<float4*>(p.partial)[(int64_t)ps * p.n4 + col[c]] = acc[c];
+      }
+    }
+  }
+
+  // ---- phase C: fixed-order sum of the pair-split partials
+  if (p.PS > 1) {
+    __threadfence();
+    grid.sync();
+    const int64_t gstride = (int64_t)gridDim.x * kThreads;
+    for (int64_t col4 = (int64_t)blockIdx.x * kThreads + tid; col4 < p.n4; col4 += gstride) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < p.PS; ++q) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(p.partial) + (int64_t)q * p.n4 + col4);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      epilogue(p, adam, col4, s);
+    }
+  }
+  if (p.fused_adam && blockIdx.x == 0 && tid == 0) p.state->adam_step = adam_t;
+}
+
+__global__ void __launch_bounds__(256) clamp_adam_kernel(const RankGradParams p) {
+  __shared__ AdamScalars s_adam;
+  const bool do_adam = p.theta != nullptr;
+  int64_t adam_t = 0;
+  if (do_adam) adam_t = p.state->adam_step + 1;
+  if (threadIdx.x == 0) {
+    AdamScalars a;
+    a.inv_div = (float)p.P;
+    a.clamp = p.adam.clamp;
+    a.one_minus_b1 = (float)(1.0 - p.adam.beta1);
+    a.b2 = (float)p.adam.beta2;
+    a.one_minus_b2 = (float)(1.0 - p.adam.beta2);
+    a.eps = (float)p.adam.eps;
+    a.wd = (float)p.adam.weight_decay;
+    a.bc2_sqrt = 1.f; a.neg_step = 0.f;
+    if (do_adam) {
+      a.bc2_sqrt = (float)sqrt(1.0 - pow(p.adam.beta2, (double)adam_t));
+      a.neg_step = (float)(-(p.adam.lr / (1.0 - pow(p.adam.beta1, (double)adam_t))));
+    }
+    s_adam = a;
+  }
+  __syncthreads();
+  const AdamScalars a = s_adam;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < p.n; k += stride) {
+    const float sum = p.grad_sum_out[k];
+    if (do_adam) {
+      float t = p.theta[k], m_ = p.m[k], v_ = p.v[k], g_;
+      adam_elem(sum, a, t, m_, v_, &g_);
+      p.theta[k] = t; p.m[k] = m_; p.v[k] = v_;
+      if (p.grad_out) p.grad_out[k] = g_;
+    } else {
+      float gp = -__fdiv_rn(sum, a.inv_div);
+      if (a.clamp > 0.f) gp = fminf(fmaxf(gp, -a.clamp), a.clamp);
+      p.grad_out[k] = gp;
+    }
+  }
+}
+// The step counter is advanced by a separate 1-thread epilogue so that no CTA
+// of clamp_adam_kernel can observe the incremented value.
+__global__ void bump_adam_step_kernel(estk_state* state) { state->adam_step += 1; }
+
+template <int NC>
+int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
+  int occ = 0;
+  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC>, kThreads, 0));
+  if (occ < 1) {
+    estk_set_error("rank_grad_kernel<%d> cannot be resident", NC);
+    return ESTK_ERR_CUDA;
+  }
+  if (occ > 4) occ = 4;  // 4 x 256 threads x 8 x 16 B in flight per SM saturates HBM
+  const int gmax = occ * ctx->sm_count;
+  const int64_t n4 = p.n4;
+  if (n4 >= (int64_t)ctx->sm_count * 512) {
+    // enough columns to keep every SM busy without splitting pairs
+    p.PS = 1;
+    p.CS = gmax;
+  } else {
+    p.CS = (int)((n4 + kThreads - 1) / kThreads);
+    int ps = gmax / p.CS;
+    const int ps_cap = (p.pairs_local + 15) / 16;  // >= 16 pair rows per CTA
+    if (ps > ps_cap) ps = ps_cap;
+    if (ps < 1) ps = 1;
+    p.PS = ps;
+    if ((int64_t)p.PS * n4 * 4 > (int64_t)ctx->max_grid * 1024) {
+      estk_set_error("rank_grad: partial workspace too small (PS=%d n4=%lld)", p.PS, (long long)n4);
+      return ESTK_ERR_NOMEM;
+    }
+  }
+  const int grid = p.CS * p.PS;
+  void* args[] = {(void*)&p};
+  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC>, dim3(grid), dim3(kThreads), args, 0, stream));
+  return ESTK_OK;
+}
+
+int check_common(estk_ctx* ctx, const float* returns, int P, const float* table,
+                 const int64_t* offsets, int64_t n, const char* who) {
+  ESTK_CHECK_ARG(ctx && returns && table && offsets, "%s: null argument", who);
+  ESTK_CHECK_ARG(P >= 2 && (P % 2) == 0 && P <= ESTK_MAX_POPULATION,
+                 "%s: population_size %d must be even, >= 2 and <= %d", who, P, ESTK_MAX_POPULATION);
+  ESTK_CHECK_ARG(n > 0, "%s: n must be positive", who);
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(table), "%s: noise table must be 16-byte aligned", who);
+  return ESTK_OK;
+}
+
+int dispatch(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
+  // NC = float4 columns per thread per pass; only matters when PS == 1
+  const int64_t per_cta = p.n4 / ((int64_t)ctx->sm_count * 4) + 1;
+  if (per_cta > kThreads) return launch_rank_grad<2>(ctx, p, stream);
+  return launch_rank_grad<1>(ctx, p, stream);
+}
+
+}  // namespace
+
+extern "C" int estk_rank_grad_adam(estk_ctx* ctx, const float* returns, const float* novelty,
+                                   float w_rew, float w_nov, int32_t P, const float* table,
+                                   const int64_t* offsets, const int32_t* order, int64_t n,
+                                   float* theta, float* m, float* v, estk_state* state,
+                                   const estk_adam_desc* adam, int32_t* ranks_out,
+                                   int32_t* ranks2_out, float* grad_out, void* stream) {
+  int rc = check_common(ctx, returns, P, table, offsets, n, "estk_rank_grad_adam");
+  if (rc) return rc;
+  ESTK_CHECK_ARG(theta && m && v && state && adam, "estk_rank_grad_adam: null optimizer argument");
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(m) && ESTK_ALIGNED16(v) &&
+                 (!grad_out || ESTK_ALIGNED16(grad_out)),
+                 "estk_rank_grad_adam: theta/m/v/grad_out must be 16-byte aligned");
+  RankGradParams p = {};
+  p.returns = returns; p.novelty = novelty; p.w_rew = w_rew; p.w_nov = w_nov;
+  p.P = P; p.pairs = P / 2; p.pair_begin = 0; p.pairs_local = P / 2;
+  p.table = table; p.offsets = offsets; p.order = order;
+  p.n = n; p.n4 = (n + 3) / 4;
+  p.cvals = ctx->cvals; p.partial = ctx->partial;
+  p.ranks_out = ranks_out; p.ranks2_out = ranks2_out;
+  p.fused_adam = 1; p.grad_out = grad_out;
+  p.theta = theta; p.m = m; p.v = v; p.state = state; p.adam = *adam;
+  return dispatch(ctx, p, (cudaStream_t)stream);
+}
+
+extern "C" int estk_rank_grad(estk_ctx* ctx, const float* returns, const float* novelty,
+                              float w_rew, float w_nov, int32_t P, const float* table,
+                              const int64_t* offsets, const int32_t* order, int32_t pair_begin,
+                              int32_t pairs_local, int64_t n, float* grad_sum_out,
+                              int32_t* ranks_out, int32_t* ranks2_out, void* stream) {
+  int rc = check_common(ctx, returns, P, table, offsets, n, "estk_rank_grad");
+  if (rc) return rc;
+  ESTK_CHECK_ARG(grad_sum_out && ESTK_ALIGNED16(grad_sum_out), "estk_rank_grad: grad_sum_out null or unaligned");
+  ESTK_CHECK_ARG(pair_begin >= 0 && pairs_local > 0 && pair_begin + pairs_local <= P / 2,
+                 "estk_rank_grad: local pairs [%d,+%d) outside %d", pair_begin, pairs_local, P / 2);
+  RankGradParams p = {};
+  p.returns = returns; p.novelty = novelty; p.w_rew = w_rew; p.w_nov = w_nov;
+  p.P = P; p.pairs = P / 2; p.pair_begin = pair_begin; p.pairs_local = pairs_local;
+  p.table = table; p.offsets = offsets; p.order = order;
+  p.n = n; p.n4 = (n + 3) / 4;
+  p.cvals = ctx->cvals; p.partial = ctx->partial;
+  p.ranks_out = ranks_out; p.ranks2_out = ranks2_out;
+  p.fused_adam = 0; p.grad_sum_out = grad_sum_out;
+  p.adam.clamp = 0.f;
+  return dispatch(ctx, p, (cudaStream_t)stream);
+}
+
+extern "C" int estk_clamp_adam(estk_ctx* ctx, const float* grad_sum, int32_t P, int64_t n,
+                               float* theta, float* m, float* v, estk_state* state,
+                               const estk_adam_desc* adam, float* grad_out, void* stream) {
+  ESTK_CHECK_ARG(ctx && grad_sum && adam, "estk_clamp_adam: null argument");
+  ESTK_CHECK_ARG(P >= 2 && n > 0, "estk_clamp_adam: bad P/n");
+  const bool do_adam = theta != nullptr;
+  ESTK_CHECK_ARG(do_adam ? (m && v && state) : (grad_out != nullptr),
+                 "estk_clamp_adam: need theta+m+v+state, or grad_out alone");
+  RankGradParams p = {};
+  p.P = P; p.n = n;
+  p.grad_sum_out = const_cast<float*>(grad_sum);
+  p.grad_out = grad_out; p.theta = theta; p.m = m; p.v = v; p.state = state; p.adam = *adam;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  clamp_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  ESTK_CUDA(cudaGetLastError());
+  if (do_adam) {
+    bump_adam_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+    ESTK_CUDA(cudaGetLastError());
+  }
+  return ESTK_OK;
+}

@@ -1,0 +1,193 @@
+/*
+ * estk.h -- C ABI of the B200 Evolution-Strategies kernel library (libestk.so).
+ *
+ * This is the drop-in boundary for the ES generation hot path of
+ * goktug97/estorch (estorch/estorch.py:211-250, ES._master).  The reference has
+ * no FFI layer of its own (pure Python); each entry point below names the
+ * reference function(s) whose arithmetic it replaces.  The only caller is the
+ * host-side mirror of the reference classes (estorch_b200/estorch.py) through
+ * ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: no C++ types, no exceptions, no torch types in any signature;
+ *   - every function returns ESTK_OK (0) or a negative estk_status; the text of
+ *     the last failure on the calling thread is estk_last_error();
+ *   - all buffers are CALLER-OWNED DEVICE pointers (fp32 / int32 / int64,
+ *     contiguous, 16-byte aligned) unless a parameter says "host";
+ *   - every launch is asynchronous on the caller's stream (`stream` is a
+ *     cudaStream_t passed as void*); the library never synchronises;
+ *   - the library keeps no global mutable state: one estk_ctx per device
+ *     holds an opaque workspace (partial sums, centred-rank scratch).
+ *
+ * Member / pair layout (estorch.py:190-193): population_size P = 2*pairs;
+ * member j < pairs is theta + sigma*T[off_j : off_j+n], member j+pairs is
+ * theta - sigma*T[off_j : off_j+n].  T is the shared unit-normal noise table.
+ */
+#ifndef ESTK_H_
+#define ESTK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ESTK_API __attribute__((visibility("default")))
+#else
+#define ESTK_API
+#endif
+
+#define ESTK_VERSION 100          /* 0.1.0 */
+#define ESTK_MAX_LAYERS 8
+#define ESTK_MAX_POPULATION 32768 /* P; rank phase is O(P^2) */
+
+typedef enum {
+  ESTK_OK = 0,
+  ESTK_ERR_INVALID = -1,      /* bad argument (shape, alignment, null) */
+  ESTK_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+  ESTK_ERR_UNSUPPORTED = -3,  /* valid request this build cannot serve */
+  ESTK_ERR_NOMEM = -4
+} estk_status;
+
+typedef struct estk_ctx estk_ctx;
+
+/* Device-resident per-run state (caller-owned, 32 bytes, zero-initialised by
+ * the caller except best_reward = -inf).  Kept on the device so that a whole
+ * generation can be replayed from a CUDA graph with no host-side scalars. */
+typedef struct {
+  int64_t generation;   /* estorch.py:248 `self.step`; read by estk_make_offsets,
+                           advanced by estk_track_best */
+  int64_t adam_step;    /* torch Adam `state['step']`; advanced by the Adam epilogue */
+  float episode_reward; /* estorch.py:182 */
+  float best_reward;    /* estorch.py:183-184 */
+  int32_t improved;     /* 1 when the last estk_track_best took a new best */
+  int32_t reserved;
+} estk_state;
+
+/* Policy description: Linear -> act -> ... -> Linear over a flat parameter
+ * vector in torch.nn.utils.parameters_to_vector order (weight [out,in]
+ * row-major, then bias, per layer) -- examples/cartpole_es.py:6-20. */
+typedef struct {
+  int32_t n_layers;                  /* number of Linear layers, 1..ESTK_MAX_LAYERS */
+  int32_t dims[ESTK_MAX_LAYERS + 1]; /* dims[0] = obs dim, dims[n_layers] = out dim */
+  int32_t activation;                /* 0 = ReLU between layers (none after the last) */
+} estk_mlp_desc;
+
+/* torch.optim.Adam hyper-parameters (torch/optim/adam.py:457-546; the
+ * optimizer every reference example uses, examples/cartpole_es.py:48-50). */
+typedef struct {
+  double lr, beta1, beta2, eps, weight_decay;
+  float clamp; /* estorch.py:243 clamps the negated gradient to +-1.0; <=0 disables */
+} estk_adam_desc;
+
+ESTK_API int estk_version(void);
+ESTK_API const char* estk_last_error(void);
+
+ESTK_API int estk_ctx_create(int device, estk_ctx** out);
+ESTK_API int estk_ctx_destroy(estk_ctx* ctx);
+/* sm_count, compute capability of the context's device (host ints). */
+ESTK_API int estk_ctx_info(estk_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- noise table (new-engine replacement of estorch.py:189-190's fresh
+ *      Normal(0,sigma).sample per generation) ---- */
+
+/* Fill table[0:len) with unit normals: Philox4x32-10(counter=i/4, key=seed)
+ * + Box-Muller.  len % 4 == 0.  Identical on every GPU for the same seed. */
+ESTK_API int estk_fill_noise_table(estk_ctx* ctx, float* table, int64_t len, uint64_t seed,
+                          void* stream);
+
+/* offsets_out[i] = 32 * (mix64(mix64(seed ^ gen*C) + pair_begin + i) mod nslots),
+ * nslots = (table_len - ceil32(n))/32 + 1.  gen = state->generation when
+ * `state` is non-null (device), else gen_host.  order_out (nullable, int32
+ * [pairs]) receives the local pair indices sorted by offset (ties by index):
+ * evaluating / reducing pairs in that order lets overlapping table rows hit L2. */
+ESTK_API int estk_make_offsets(estk_ctx* ctx, uint64_t seed, const estk_state* state, int64_t gen_host,
+                      int64_t pair_begin, int32_t pairs, int64_t table_len, int64_t n,
+                      int64_t* offsets_out, int32_t* order_out, void* stream);
+
+/* Materialise population rows (estorch.py:187-193 `_sample_policy`):
+ * for m in [member_begin, member_begin+member_count): rows_out[m-member_begin] =
+ * theta +- sigma*T[off], eps_out (nullable) = +-sigma*T[off].  P = 2*pairs. */
+ESTK_API int estk_perturb_rows(estk_ctx* ctx, const float* theta, int64_t n, const float* table,
+                      const int64_t* offsets, int32_t pairs, float sigma,
+                      int32_t member_begin, int32_t member_count,
+                      float* rows_out, float* eps_out, void* stream);
+
+/* ---- kernel 1: population evaluate (estorch.py:195-202 `_calculate_returns`
+ *      + Policy.forward examples/cartpole_es.py:14-20 + the synthetic agent
+ *      return -mean((policy(obs)-target)^2)) ---- */
+
+/* For each local pair j: returns_plus[j] / returns_minus[j] = return of
+ * theta +/- sigma*T[offsets[j]].  obs [B, dims[0]], target [B, dims[L]] fp32
+ * row-major.  bc_plus/bc_minus (nullable) [pairs, bc_dim] receive the behaviour
+ * characteristic policy(obs[:bc_obs]).flatten()[:bc_dim] (examples/nsra_es.py:45-49).
+ * order (nullable) = evaluation order from estk_make_offsets. */
+ESTK_API int estk_eval_mlp(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                  const float* table, const int64_t* offsets, const int32_t* order,
+                  int32_t pairs, float sigma, const float* obs, const float* target, int32_t B,
+                  float* returns_plus, float* returns_minus,
+                  float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim,
+                  void* stream);
+
+/* Unperturbed policy (estorch.py:181-182 `_after_optimize` rollout):
+ * return_out[0] = return of theta; bc_out (nullable) [bc_dim]. */
+ESTK_API int estk_eval_mlp_center(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                         const float* obs, const float* target, int32_t B,
+                         float* return_out, float* bc_out, int32_t bc_obs, int32_t bc_dim,
+                         void* stream);
+
+/* estorch.py:182-185: episode_reward = *reward; if it beats state->best_reward,
+ * take it and copy theta -> best_theta (the device analogue of
+ * deepcopy(state_dict())).  Also advances state->generation (estorch.py:248). */
+ESTK_API int estk_track_best(estk_ctx* ctx, estk_state* state, const float* reward,
+                    const float* theta, float* best_theta, int64_t n, void* stream);
+
+/* ---- kernel 2: centred-rank transform + weighted noise reduction + Adam
+ *      (estorch.py:15-39 rank_transformation, :174-179 _calculate_grad and the
+ *      NS/NSR/NSRA variants :419-425/:542-549/:640-648, :236-244 negate+clamp,
+ *      :245 optimizer.step -> torch Adam) ---- */
+
+/* Single-GPU fused form.  returns [P] (reward column), novelty [P] or NULL.
+ * Blend row c = w_rew*c(reward) + w_nov*c(novelty) in fp32 when novelty is
+ * given (ES: novelty NULL -> c(reward)).  Ranks are bit-exact vs
+ * _compute_ranks on tie-free input (ties: stable by member index); centring in
+ * fp64 then fp32 as estorch.py:17-19,:176.
+ *   g = (1/P) * sum_j (c_j - c_{j+pairs}) * T[off_j : off_j+n]
+ * then grad = clamp(-g), Adam(theta, m, v) in place; state->adam_step += 1.
+ * ranks_out / ranks2_out (nullable, int32 [P]) and grad_out (nullable, fp32
+ * [n], the reference's un-negated estimate) are for inspection / parity. */
+ESTK_API int estk_rank_grad_adam(estk_ctx* ctx, const float* returns, const float* novelty,
+                        float w_rew, float w_nov, int32_t P,
+                        const float* table, const int64_t* offsets, const int32_t* order,
+                        int64_t n, float* theta, float* m, float* v, estk_state* state,
+                        const estk_adam_desc* adam,
+                        int32_t* ranks_out, int32_t* ranks2_out, float* grad_out, void* stream);
+
+/* Multi-GPU form: same rank phase over all P returns, reduction over the local
+ * pairs [pair_begin, pair_begin+pairs_local) only; grad_sum_out[n] receives the
+ * RAW partial sum (no 1/P) to be all-reduced (SUM) by the caller
+ * (replaces the Send/Recv star of estorch.py:207-233). */
+ESTK_API int estk_rank_grad(estk_ctx* ctx, const float* returns, const float* novelty,
+                   float w_rew, float w_nov, int32_t P,
+                   const float* table, const int64_t* offsets, const int32_t* order,
+                   int32_t pair_begin, int32_t pairs_local, int64_t n,
+                   float* grad_sum_out, int32_t* ranks_out, int32_t* ranks2_out, void* stream);
+
+/* Epilogue on an all-reduced raw sum: g = grad_sum / P, negate, clamp, Adam.
+ * theta/m/v NULL with grad_out set = gradient only (for non-Adam optimizers:
+ * grad_out then receives clamp(-g), the tensor the reference stores in .grad). */
+ESTK_API int estk_clamp_adam(estk_ctx* ctx, const float* grad_sum, int32_t P, int64_t n,
+                    float* theta, float* m, float* v, estk_state* state,
+                    const estk_adam_desc* adam, float* grad_out, void* stream);
+
+/* ---- novelty (estorch.py:412-417): nov[i] = sum of the k smallest euclidean
+ *      distances from bc[i] to the archive rows / ||archive||_F ---- */
+ESTK_API int estk_knn_novelty(estk_ctx* ctx, const float* bc, int32_t count, const float* archive,
+                     int32_t archive_len, int32_t dim, int32_t k, float* novelty_out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESTK_H_ */

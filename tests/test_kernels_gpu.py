@@ -1,0 +1,349 @@
+"""Kernel-level parity: every C-ABI entry point vs the CPU oracle / the
+reference-generated goldens, through the ctypes binding (estorch_b200.backend).
+
+Tolerances: integer outputs (offsets, order, ranks) bit-exact; materialised
+rows bit-exact (same two fp32 roundings as the reference); fp32 reductions
+within 1e-5 max-norm relative (max|a-b| <= 1e-5 * max|b|).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import es_oracle as orc
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    from estorch_b200.backend import CudaBackend
+    return CudaBackend(torch.device("cuda", 0))
+
+
+def dev(be, a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(be.device)
+
+
+# ------------------------------------------------------------------ noise
+def test_fill_noise_table_matches_oracle(be):
+    n = 1 << 16
+    t = be.alloc(n)
+    be.fill_noise_table(t, 42)
+    got = t.cpu().numpy()
+    want = orc.philox_normal_table(n, 42)
+    # fp32 log/sincos differ by ulps between libm and the device: |z| < 6
+    assert np.max(np.abs(got - want)) < 2e-5
+    big = be.alloc(1 << 24)
+    be.fill_noise_table(big, (7 << 32) | 9)
+    assert abs(float(big.mean())) < 2e-3 and abs(float(big.std()) - 1.0) < 2e-3
+    assert torch.isfinite(big).all()
+    np.testing.assert_allclose(big[:4096].cpu().numpy(), orc.philox_normal_table(4096, (7 << 32) | 9), atol=2e-5)
+
+
+@pytest.mark.parametrize("pairs,n,table_len,pair_begin,gen", [
+    (32, 4610, 1 << 15, 0, 0), (2048, 4610, 1 << 20, 0, 3), (512, 1001760, 1 << 22, 1024, 17),
+    (5, 7, 64, 0, 1), (8192, 6020, 1 << 24, 8192, 2)])
+def test_make_offsets_bit_exact(be, pairs, n, table_len, pair_begin, gen):
+    from estorch_b200.backend import new_state, write_state
+    offs = be.alloc(pairs, dtype=torch.int64)
+    order = be.alloc(pairs, dtype=torch.int32)
+    be.make_offsets(0xDEADBEEF12345, None, gen, pair_begin, pairs, table_len, n, offs, order)
+    want = orc.noise_offsets(0xDEADBEEF12345, gen, pair_begin, pairs, table_len, n)
+    np.testing.assert_array_equal(offs.cpu().numpy(), want)
+    np.testing.assert_array_equal(order.cpu().numpy(), np.argsort(want, kind="stable").astype(np.int32))
+    # generation read from the device-resident state
+    st = new_state(be.device)
+    write_state(st, generation=gen)
+    offs2 = be.alloc(pairs, dtype=torch.int64)
+    be.make_offsets(0xDEADBEEF12345, st, -1, pair_begin, pairs, table_len, n, offs2, None)
+    np.testing.assert_array_equal(offs2.cpu().numpy(), want)
+
+
+def test_perturb_rows_bit_exact(be):
+    g = load_golden("es_cartpole_p64.npz")
+    theta, table, offs = g["theta0"], g["table"], g["offsets"][0]
+    P, n = 64, theta.size
+    rows = be.alloc(P, n)
+    eps = be.alloc(P, n)
+    be.perturb_rows(dev(be, theta), dev(be, table), dev(be, offs), P // 2, 0.1, 0, P, rows, eps)
+    pop, epsilon = orc.sample_population(theta, table, offs, 0.1)
+    np.testing.assert_array_equal(rows.cpu().numpy(), pop)
+    np.testing.assert_array_equal(eps.cpu().numpy(), epsilon)
+    part = be.alloc(5, n)
+    be.perturb_rows(dev(be, theta), dev(be, table), dev(be, offs), P // 2, 0.1, 30, 5, part, None)
+    np.testing.assert_array_equal(part.cpu().numpy(), pop[30:35])
+
+
+# ------------------------------------------------------------------ evaluate
+def _eval(be, dims, theta, table, offs, sigma, obs, tgt, order=None, bc_obs=0, bc_dim=0):
+    pairs = len(offs)
+    ret = be.zeros(2 * pairs)
+    bcp = be.zeros(pairs, bc_dim) if bc_dim else None
+    bcm = be.zeros(pairs, bc_dim) if bc_dim else None
+    be.eval_mlp(dims, dev(be, theta), dev(be, table), dev(be, offs),
+                None if order is None else dev(be, order), pairs, sigma, dev(be, obs), dev(be, tgt),
+                ret[:pairs], ret[pairs:], bcp, bcm, bc_obs, bc_dim)
+    torch.cuda.synchronize()
+    bcs = None if not bc_dim else np.concatenate([bcp.cpu().numpy(), bcm.cpu().numpy()])
+    return ret.cpu().numpy(), bcs
+
+
+def test_eval_mlp_matches_reference_golden(be):
+    g = load_golden("es_cartpole_p64.npz")
+    dims = [int(d) for d in g["dims"]]
+    for gen in range(3):
+        ret, _ = _eval(be, dims, g["theta_before"][gen], g["table"], g["offsets"][gen], 0.1,
+                       g["obs"], g["target"])
+        ref = g["returns"][gen][:, 0]          # produced by the unmodified reference
+        assert rel_err(ret, ref) < 2e-6
+    # evaluation order must not change results
+    order = np.argsort(g["offsets"][0], kind="stable").astype(np.int32)
+    ret2, _ = _eval(be, dims, g["theta_before"][0], g["table"], g["offsets"][0], 0.1,
+                    g["obs"], g["target"], order=order)
+    ret1, _ = _eval(be, dims, g["theta_before"][0], g["table"], g["offsets"][0], 0.1,
+                    g["obs"], g["target"])
+    np.testing.assert_array_equal(ret1, ret2)
+
+
+def test_eval_mlp_tiny_and_ragged(be):
+    g = load_golden("es_tiny_p8.npz")
+    dims = [int(d) for d in g["dims"]]
+    ret, _ = _eval(be, dims, g["theta_before"][0], g["table"], g["offsets"][0], 0.05,
+                   g["obs"], g["target"])                       # B = 5: ragged chunk
+    assert rel_err(ret, g["returns"][0][:, 0]) < 2e-6
+
+
+def test_eval_mlp_bc_matches_reference_golden(be):
+    g = load_golden("nsra_bipedal_p32.npz")
+    dims = [int(d) for d in g["dims"]]
+    theta, offs = g["theta_before"][0], g["offsets"][0]
+    ret, bcs = _eval(be, dims, theta, g["table"], offs, 0.02, g["obs"], g["target"],
+                     bc_obs=int(g["bc_obs"]), bc_dim=int(g["bc_dim"]))
+    assert rel_err(ret, g["returns"][0][:, 0]) < 2e-6
+    pop, _ = orc.sample_population(theta, g["table"], offs, 0.02)
+    _, want_bc = orc.evaluate_population(pop, dims, g["obs"], g["target"], 64, 256)
+    assert rel_err(bcs, want_bc) < 2e-6
+
+
+@pytest.mark.parametrize("dims,B,pairs", [([128, 512, 512, 288], 48, 4), ([17, 33, 5], 100, 6),
+                                          ([4, 2], 1, 3), ([9, 130, 70, 70, 3], 256, 3)])
+def test_eval_mlp_shapes_vs_oracle(be, dims, B, pairs):
+    rng = np.random.RandomState(1)
+    n = orc.mlp_param_count(dims)
+    table_len = max(1 << 14, (n + 31) // 32 * 32 + 4096)
+    table = rng.standard_normal(table_len).astype(np.float32)
+    theta = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    obs = rng.standard_normal((B, dims[0])).astype(np.float32)
+    tgt = rng.standard_normal((B, dims[-1])).astype(np.float32)
+    offs = orc.noise_offsets(5, 0, 0, pairs, table_len, n)
+    ret, _ = _eval(be, dims, theta, table, offs, 0.02, obs, tgt)
+    pop, _ = orc.sample_population(theta, table, offs, 0.02)
+    want, _ = orc.evaluate_population(pop, dims, obs, tgt)
+    assert rel_err(ret, want) < 5e-6
+    one = be.zeros(1)
+    be.eval_mlp_center(dims, dev(be, theta), dev(be, obs), dev(be, tgt), one)
+    assert abs(float(one) - float(orc.synthetic_return(orc.mlp_forward(theta, dims, obs), tgt))) \
+        < 5e-6 * abs(float(one)) + 1e-7
+
+
+# ------------------------------------------------------------------ rank + grad + Adam
+def _rank_grad_adam(be, returns, table, offs, theta, m, v, step, novelty=None, w=(1.0, 0.0),
+                    order=None, lr=0.01):
+    from estorch_b200.backend import new_state, write_state, read_state, adam_desc
+    P, n = returns.size, theta.size
+    st = new_state(be.device)
+    write_state(st, adam_step=step)
+    th, mm, vv = dev(be, theta), dev(be, m), dev(be, v)
+    ranks = be.zeros(P, dtype=torch.int32)
+    ranks2 = be.zeros(P, dtype=torch.int32) if novelty is not None else None
+    grad = be.zeros(n)
+    be.rank_grad_adam(dev(be, returns), None if novelty is None else dev(be, novelty), w[0], w[1], P,
+                      dev(be, table), dev(be, offs), None if order is None else dev(be, order),
+                      th, mm, vv, st, adam_desc(lr=lr), ranks, ranks2, grad)
+    torch.cuda.synchronize()
+    assert read_state(st)["adam_step"] == step + 1
+    return dict(ranks=ranks.cpu().numpy(), ranks2=None if ranks2 is None else ranks2.cpu().numpy(),
+                grad=grad.cpu().numpy(), theta=th.cpu().numpy(), m=mm.cpu().numpy(), v=vv.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["es_tiny_p8.npz", "es_cartpole_p64.npz"])
+def test_rank_grad_adam_matches_reference_golden(be, name):
+    g = load_golden(name)
+    n = g["theta0"].size
+    theta, m, v = g["theta0"].copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for gen in range(len(g["grad"])):
+        ret = np.ascontiguousarray(g["returns"][gen][:, 0])     # the reference's return bits
+        out = _rank_grad_adam(be, ret, g["table"], g["offsets"][gen], theta, m, v, gen)
+        np.testing.assert_array_equal(out["ranks"], orc.compute_ranks(ret))       # bit-exact
+        assert rel_err(out["grad"], g["grad"][gen]) < 1e-5
+        ok = np.abs(g["grad"][gen]) > 1e-4 * np.abs(g["grad"][gen]).max()      # see DESIGN.md (Adam at g~0)
+        assert rel_err(out["theta"][ok], g["theta_after"][gen][ok]) < 1e-5
+        assert np.abs(out["theta"] - g["theta_after"][gen]).max() <= 0.02
+        # Adam alone (identical gradient bits through clamp_adam) is exact to 1e-6
+        from estorch_b200.backend import new_state, write_state, adam_desc
+        st = new_state(be.device); write_state(st, adam_step=gen)
+        th, mm, vv = dev(be, theta), dev(be, m), dev(be, v)
+        be.clamp_adam(dev(be, g["grad"][gen] * np.float32(len(ret))), len(ret), th, mm, vv, st,
+                      adam_desc(lr=0.01))
+        assert rel_err(th.cpu().numpy(), g["theta_after"][gen]) < 1e-6
+        theta, m, v = th.cpu().numpy(), mm.cpu().numpy(), vv.cpu().numpy()
+    assert rel_err(m, g["m_final"]) < 1e-5 and rel_err(v, g["v_final"]) < 1e-5
+
+
+@pytest.mark.parametrize("algo,w", [("ns", (0.0, 1.0)), ("nsr", (0.5, 0.5)), ("nsra", None)])
+def test_rank_grad_ns_blends_match_reference_golden(be, algo, w):
+    g = load_golden(f"{algo}_bipedal_p32.npz")
+    n = g["meta_theta0"].shape[1]
+    for gen in range(len(g["grad"])):
+        ret = g["returns"][gen]
+        if algo == "nsra":
+            wt = float(g["weight"][gen - 1]) if gen > 0 else 1.0   # weight in force during this generation
+            ww = (np.float32(wt), np.float32(1.0 - wt))
+        else:
+            ww = w
+        out = _rank_grad_adam(be, np.ascontiguousarray(ret[:, 0]), g["table"], g["offsets"][gen],
+                              g["theta_before"][gen], np.zeros(n, np.float32), np.zeros(n, np.float32),
+                              0, novelty=np.ascontiguousarray(ret[:, 1]), w=ww)
+        np.testing.assert_array_equal(out["ranks"], orc.compute_ranks(ret[:, 0]))
+        np.testing.assert_array_equal(out["ranks2"], orc.compute_ranks(ret[:, 1]))
+        assert rel_err(out["grad"], g["grad"][gen]) < 1e-5
+
+
+@pytest.mark.parametrize("n,P", [(7, 8), (4610, 4096), (400003, 64), (1001760, 32)])
+def test_rank_grad_adam_sizes_vs_oracle(be, n, P):
+    rng = np.random.RandomState(n)
+    table_len = (n + 31) // 32 * 32 + (1 << 16)
+    table = rng.standard_normal(table_len).astype(np.float32)
+    offs = orc.noise_offsets(3, 1, 0, P // 2, table_len, n)
+    ret = rng.standard_normal(P).astype(np.float32)
+    assert len(np.unique(ret)) == P
+    theta = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    m = (rng.standard_normal(n) * 0.01).astype(np.float32)
+    v = (rng.random(n) * 1e-3).astype(np.float32)
+    order = np.argsort(offs, kind="stable").astype(np.int32)
+    out = _rank_grad_adam(be, ret, table, offs, theta, m, v, 5, order=order)
+    np.testing.assert_array_equal(out["ranks"], orc.compute_ranks(ret))
+    want = orc.calculate_grad_pairs(ret, table, offs, n)
+    assert rel_err(out["grad"], want) < 1e-5
+    th, mm, vv = orc.adam_step(theta, m, v, orc.negate_clamp(out["grad"]), 6)
+    assert rel_err(out["theta"], th) < 1e-6 and rel_err(out["m"], mm) < 1e-6 and rel_err(out["v"], vv) < 1e-6
+    # same result without the sorted order (summation order changes: 1e-6)
+    out2 = _rank_grad_adam(be, ret, table, offs, theta, m, v, 5)
+    assert rel_err(out2["grad"], out["grad"]) < 2e-6
+
+
+def test_rank_ties_stable_by_index(be):
+    ret = np.array([1.0, 0.0, 1.0, 0.0, 2.0, 2.0, -1.0, 0.0], dtype=np.float32)
+    table = np.random.RandomState(0).standard_normal(4096).astype(np.float32)
+    offs = orc.noise_offsets(1, 0, 0, 4, 4096, 16)
+    out = _rank_grad_adam(be, ret, table, offs, np.zeros(16, np.float32), np.zeros(16, np.float32),
+                          np.zeros(16, np.float32), 0)
+    np.testing.assert_array_equal(out["ranks"], orc.compute_ranks(ret))
+
+
+def test_sharded_rank_grad_equals_fused(be):
+    """Multi-GPU form on one GPU: sum of per-shard raw partials -> clamp_adam
+    equals the fused kernel (this is what the NCCL all-reduce computes)."""
+    from estorch_b200.backend import new_state, write_state, adam_desc
+    rng = np.random.RandomState(9)
+    n, P, W = 6020, 256, 4
+    table_len = 1 << 16
+    table = rng.standard_normal(table_len).astype(np.float32)
+    offs = orc.noise_offsets(3, 2, 0, P // 2, table_len, n)
+    ret = rng.standard_normal(P).astype(np.float32)
+    theta = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    zeros = np.zeros(n, np.float32)
+    fused = _rank_grad_adam(be, ret, table, offs, theta, zeros, zeros, 0)
+    pl = P // 2 // W
+    total = be.zeros(n)
+    for r in range(W):
+        part = be.zeros(n)
+        ranks = be.zeros(P, dtype=torch.int32)
+        be.rank_grad(dev(be, ret), None, 1.0, 0.0, P, dev(be, table), dev(be, offs[r * pl:(r + 1) * pl]),
+                     None, r * pl, pl, n, part, ranks)
+        total += part
+        np.testing.assert_array_equal(ranks.cpu().numpy(), fused["ranks"])
+    st = new_state(be.device)
+    th, mm, vv = dev(be, theta), dev(be, zeros), dev(be, zeros)
+    gout = be.zeros(n)
+    be.clamp_adam(total, P, th, mm, vv, st, adam_desc(lr=0.01), gout)
+    assert rel_err(gout.cpu().numpy(), fused["grad"]) < 2e-6
+    ok = np.abs(fused["grad"]) > 1e-4 * np.abs(fused["grad"]).max()
+    assert rel_err(th.cpu().numpy()[ok], fused["theta"][ok]) < 1e-5
+    # gradient-only epilogue (non-Adam optimizers): clamp(-g)
+    gonly = be.zeros(n)
+    be.clamp_adam(total, P, None, None, None, None, adam_desc(), gonly)
+    np.testing.assert_allclose(gonly.cpu().numpy(), orc.negate_clamp(gout.cpu().numpy()), rtol=0, atol=0)
+
+
+def test_full_size_north_star_gradient_property(be):
+    """P=4096, n=1,001,760 (BASELINE north star): the kernel's gradient equals an
+    independent on-device evaluation of sum_j w_j T[off_j:off_j+n] (torch fp64
+    gather-matmul in chunks), and negating the returns negates the gradient."""
+    from estorch_b200.backend import new_state, adam_desc
+    n, P = 1001760, 4096
+    pairs = P // 2
+    table_len = 1 << 26
+    table = be.alloc(table_len)
+    be.fill_noise_table(table, 42)
+    offs = be.alloc(pairs, dtype=torch.int64)
+    order = be.alloc(pairs, dtype=torch.int32)
+    be.make_offsets(42, None, 0, 0, pairs, table_len, n, offs, order)
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    ret = torch.randn(P, generator=gen).to(be.device)
+    assert ret.unique().numel() == P
+    zeros = lambda: be.zeros(n)
+    out = {}
+    for sign in (1.0, -1.0):
+        th, m, v, g = zeros(), zeros(), zeros(), zeros()
+        ranks = be.zeros(P, dtype=torch.int32)
+        be.rank_grad_adam((ret * sign).contiguous(), None, 1.0, 0.0, P, table, offs, order, th, m, v,
+                          new_state(be.device), adam_desc(lr=0.01), ranks, None, g)
+        out[sign] = (g, ranks, th)
+    g, ranks, th = out[1.0]
+    want_ranks = torch.empty(P, dtype=torch.int64, device=be.device)
+    want_ranks[torch.argsort(ret, stable=True)] = torch.arange(P, device=be.device)
+    assert torch.equal(ranks.long(), want_ranks)
+    c = (want_ranks.double() / (P - 1) - 0.5).float()
+    w = (c[:pairs] - c[pairs:]).double()
+    acc = torch.zeros(n, dtype=torch.float64, device=be.device)
+    idx = torch.arange(n, device=be.device)
+    for j0 in range(0, pairs, 64):
+        rows = table[(offs[j0:j0 + 64, None] + idx[None, :])].double()
+        acc += w[j0:j0 + 64] @ rows
+    want = (acc / P).float()
+    assert float((g - want).abs().max() / want.abs().max()) < 1e-5
+    assert float((out[-1.0][0] + g).abs().max() / g.abs().max()) < 1e-6
+    # first Adam step from zero state moves every parameter by ~lr*sign(-g)
+    ok = g.abs() > 1e-4 * g.abs().max()
+    assert float((th[ok] + 0.01 * torch.sign(-g[ok])).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------ misc
+def test_knn_novelty_matches_oracle(be):
+    rng = np.random.RandomState(2)
+    for A, k in ((3, 10), (40, 10), (200, 5)):
+        arch = rng.standard_normal((A, 256)).astype(np.float32)
+        bc = rng.standard_normal((33, 256)).astype(np.float32)
+        out = be.zeros(33)
+        be.knn_novelty(dev(be, bc), dev(be, arch), k, out)
+        want = np.array([orc.novelty(bc[i], arch, k) for i in range(33)], dtype=np.float32)
+        assert rel_err(out.cpu().numpy(), want) < 1e-6
+
+
+def test_track_best(be):
+    from estorch_b200.backend import new_state, read_state
+    st = new_state(be.device)
+    theta, best = be.zeros(1000), be.zeros(1000)
+    for step, (r, improves) in enumerate([(-3.0, True), (-5.0, False), (-1.0, True)]):
+        theta.fill_(float(step + 1))
+        be.track_best(st, torch.tensor([r], device=be.device), theta, best)
+        s = read_state(st)
+        assert s["generation"] == step + 1 and s["improved"] == int(improves)
+        assert s["episode_reward"] == r
+    assert read_state(st)["best_reward"] == -1.0
+    assert float(best.min()) == 3.0 and float(best.max()) == 3.0
