@@ -1,0 +1,827 @@
+"""Host-side mirror of the reference's algorithm classes (estorch/estorch.py).
+
+Same class names, constructor signatures, ``train`` / ``terminate`` / ``log``
+API, overridable hooks and public attributes as the reference, but
+the body of a generation runs on the GPU through the C ABI in include/estk.h:
+
+    reference (CPU, estorch.py)                 here (B200)
+    -------------------------------------------  ------------------------------------------
+    _sample_policy :187-193  fresh RNG + cats    noise-table offsets (estk_make_offsets)
+    MPI Send/Recv of P x n rows :207-233         nothing to send: every rank regenerates rows
+    _calculate_returns :195-202 (python loop)    estk_eval_mlp (fused) | host rollouts (plumbing)
+    rank_transformation + torch.mm :174-179      estk_rank_grad[_adam] (+ one NCCL all-reduce)
+    grad scatter/clamp :236-244, Adam.step :245  fused Adam epilogue (or torch optimizer.step)
+    _after_optimize :181-185                     estk_eval_mlp_center + estk_track_best
+
+Two execution modes, chosen per instance:
+
+* fused  -- DeviceAgent + recognised MLP policy + torch.optim.Adam + no hook
+            overridden: a generation is a handful of kernel launches, nothing
+            touches the host unless the user reads an attribute.
+* hooks  -- anything else (host agents such as gym loops, custom subclasses
+            overriding ``_sample_policy`` / ``_calculate_grad`` / ..., other
+            optimizers): the reference's own control flow through its hooks,
+            with noise rows and the gradient still produced on the device.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+from collections import OrderedDict
+from enum import Enum
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .agents import DeviceAgent
+from .backend import adam_desc, new_state, read_state, write_state
+from .policy_spec import mlp_spec_from_module
+from .population import LazyPopulation, NoiseHandle
+
+__all__ = ["ES", "NS_ES", "NSR_ES", "NSRA_ES", "rank_transformation"]
+
+DEFAULT_NOISE_TABLE_SIZE = 1 << 28   # fp32 unit normals = 1 GiB per GPU
+
+
+# ----------------------------------------------------------------------------
+# rank transform (public helper, estorch.py:15-39) -- host numpy; the device
+# path computes the same quantity inside estk_rank_grad*.
+# ----------------------------------------------------------------------------
+def _compute_ranks(rewards):
+    r = np.asarray(rewards).reshape(-1)
+    ranks = np.empty(r.size, dtype=int)
+    ranks[np.argsort(r, kind="stable")] = np.arange(r.size)
+    return ranks
+
+
+def rank_transformation(rewards):
+    """Centred ranks in [-0.5, 0.5] (float64), lowest reward -> -0.5.
+
+    >>> rank_transformation([-123, -50, 3, -5, 20, 10, 100])
+    array([-0.5, -0.33333333, 0., -0.16666667, 0.33333333, 0.16666667, 0.5])
+    Ties are broken by index (the reference leaves them unspecified).
+    """
+    ranks = _compute_ranks(rewards)
+    size = ranks.size
+    return (np.arange(size) / (size - 1) - 0.5)[ranks]
+
+
+class _Algorithm(Enum):
+    classic = 1
+    novelty = 2
+
+
+def _builtin(fn):
+    fn._estk_builtin = True
+    return fn
+
+
+def _dist_env():
+    """(rank, world, local_rank) of this process; one process per GPU."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", dist.get_rank()))
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)),
+            int(os.environ.get("LOCAL_RANK", 0)))
+
+
+class _PolicySlot:
+    """One (policy, optimizer) pair with device-resident flat state."""
+
+    def __init__(self, module, optimizer, be, flatten: bool):
+        self.module = module
+        self.optimizer = optimizer
+        self.be = be
+        params = list(module.parameters())
+        self.n = sum(p.numel() for p in params)
+        self.theta = be.zeros(self.n)
+        self.m = be.zeros(self.n)
+        self.v = be.zeros(self.n)
+        self.best_theta = be.zeros(self.n)
+        self.theta_prev = be.zeros(self.n)     # centre of the last sampled population
+        self.state = new_state(be.device)
+        self.flattened = flatten
+        with torch.no_grad():
+            self.theta.copy_(torch.nn.utils.parameters_to_vector(params).detach().to(be.device))
+            if flatten:
+                # parameters become views of the flat vector: the module always
+                # shows the live theta, no per-generation copies
+                idx = 0
+                for p in params:
+                    p.data = self.theta[idx: idx + p.numel()].view(p.shape)
+                    idx += p.numel()
+
+    def ensure_flat(self):
+        """Re-establish parameter <-> flat-vector aliasing if user code re-pointed
+        ``param.data`` (``torch.nn.utils.vector_to_parameters`` does exactly that)."""
+        if not self.flattened:
+            return
+        idx, esz = 0, self.theta.element_size()
+        with torch.no_grad():
+            for p in self.module.parameters():
+                sz = p.numel()
+                if p.data.data_ptr() != self.theta.data_ptr() + idx * esz or p.device != self.theta.device:
+                    self.theta[idx: idx + sz].copy_(p.data.reshape(-1))
+                    p.data = self.theta[idx: idx + sz].view(p.shape)
+                idx += sz
+
+    def push_theta(self):
+        """module -> flat (hooks mode: the torch optimizer updated the module)."""
+        if not self.flattened:
+            with torch.no_grad():
+                self.theta.copy_(torch.nn.utils.parameters_to_vector(self.module.parameters())
+                                 .detach().to(self.be.device))
+
+    def mirror_adam_state(self):
+        """Expose the fused Adam moments through the torch optimizer object."""
+        if not self.flattened:
+            return
+        step = float(read_state(self.state)["adam_step"])
+        idx = 0
+        for p in self.module.parameters():
+            sz = p.numel()
+            self.optimizer.state[p] = {"step": torch.tensor(step),
+                                       "exp_avg": self.m[idx: idx + sz].view(p.shape),
+                                       "exp_avg_sq": self.v[idx: idx + sz].view(p.shape)}
+            idx += sz
+
+
+class ES:
+    """Classic Evolution Strategy (OpenAI-ES, Salimans et al. 2017) with the
+    constructor and training API of the reference ``estorch.ES``
+    (estorch.py:68-308).
+
+    Args (identical to the reference, estorch.py:121-123):
+        policy: ``nn.Module`` *class*; instantiated as ``policy(**policy_kwargs)``.
+        agent: class with ``rollout(policy) -> float``; ``agent(**agent_kwargs)``.
+        optimizer: ``torch.optim`` class; ``optimizer(params, **optimizer_kwargs)``.
+        population_size: total evaluations per generation (both mirrored halves).
+        sigma: noise standard deviation.
+        device: device of the modules handed to a *host* agent's ``rollout``.
+    Engine options (keyword-only, all optional):
+        noise_table_size: length of the shared unit-normal table (default 2**28).
+        noise_seed: seed of the table and of the per-generation offsets.
+        log_interval: call ``log()`` every k-th generation only (default 1 =
+            reference behaviour).
+    Attributes as documented at estorch.py:108-117.
+    """
+
+    _ALGORITHM_TYPE = _Algorithm.classic
+
+    def __init__(self, policy, agent, optimizer, population_size, sigma=0.01,
+                 device=torch.device("cpu"), policy_kwargs={}, agent_kwargs={},
+                 optimizer_kwargs={}, *, noise_table_size=None, noise_seed=42,
+                 log_interval=1, _backend=None):
+        self.rank, self.n_workers, self._local_rank = _dist_env()
+        self.population_size = int(population_size)
+        assert not (self.population_size % self.n_workers)           # estorch.py:130
+        if self.population_size % 2 or self.population_size < 2:
+            raise ValueError("population_size must be even (mirrored sampling, estorch.py:190)")
+        if (self.population_size // 2) % self.n_workers:
+            raise ValueError("population_size/2 antithetic pairs must divide evenly over the GPUs")
+        self.device = torch.device(device)
+        self.sigma = sigma
+        self._stop = False
+        self._trained = False
+        self._noise_seed = int(noise_seed)
+        self._log_interval = max(1, int(log_interval))
+        self._policy_cls, self._policy_kwargs = policy, dict(policy_kwargs)
+        self._optimizer_cls, self._optimizer_kwargs = optimizer, dict(optimizer_kwargs)
+
+        if _backend is None:
+            from .backend import CudaBackend       # raises loudly without a GPU / the .so
+            _backend = CudaBackend(torch.device("cuda", self._local_rank % max(1, torch.cuda.device_count())))
+        self._be = _backend
+        self._dev = self._be.device
+
+        self.agent = agent(**agent_kwargs)
+        self._device_agent = isinstance(self.agent, DeviceAgent)
+        self.target = policy(**policy_kwargs).to(self.device)       # estorch.py:142
+        parameters = torch.nn.utils.parameters_to_vector(self.target.parameters())
+        self.n_parameters = parameters.shape[0]
+        self._spec = mlp_spec_from_module(self.target)
+        self._fused = self._decide_fused(optimizer)
+        self._host_cache = {}
+
+        # ---- noise table (replicated on every GPU, identical by construction)
+        n_pad = (self.n_parameters + 31) // 32 * 32
+        size = DEFAULT_NOISE_TABLE_SIZE if noise_table_size is None else int(noise_table_size)
+        size = max(size, n_pad + 32) // 32 * 32
+        self._table = self._be.alloc(size)
+        self._be.fill_noise_table(self._table, self._noise_seed)
+
+        # ---- population bookkeeping
+        P, W = self.population_size, self.n_workers
+        self._pairs = P // 2
+        self._pairs_local = self._pairs // W
+        self._pair_begin = self.rank * self._pairs_local
+        be = self._be
+        self._offsets = be.zeros(self._pairs_local, dtype=torch.int64)
+        self._order = be.zeros(self._pairs_local, dtype=torch.int32)
+        self._offsets_all = self._offsets if W == 1 else be.zeros(self._pairs, dtype=torch.int64)
+        self._returns = be.zeros(P)
+        self._novelty = None
+        self._ranks = be.zeros(P, dtype=torch.int32)
+        self._ranks2 = None
+        self._grad = be.zeros(self.n_parameters)
+        self._episode = be.zeros(1)
+        self._obs = self._tgt = None
+        if self._device_agent:
+            self._obs = self.agent.obs.to(self._dev).contiguous()
+            self._tgt = self.agent.target.to(self._dev).contiguous()
+
+        self._slots = []
+        if self._ALGORITHM_TYPE == _Algorithm.classic:
+            self.policy = self._make_module()                       # estorch.py:136
+            self.optimizer = optimizer(self.policy.parameters(), **optimizer_kwargs)   # :137
+            self._slots.append(_PolicySlot(self.policy, self.optimizer, be, self._fused))
+        self._active = self._slots[0] if self._slots else None
+        self.step = 0
+
+    # ------------------------------------------------------------------ setup helpers
+    def _make_module(self):
+        module = self._policy_cls(**self._policy_kwargs)
+        return module.to(self._dev if self._fused else self.device)
+
+    def _hook_overridden(self, name):
+        return not getattr(getattr(type(self), name), "_estk_builtin", False)
+
+    def _decide_fused(self, optimizer_cls):
+        if not self._device_agent or self._spec is None:
+            return False
+        if optimizer_cls is not torch.optim.Adam:
+            return False
+        kw = self._optimizer_kwargs
+        if kw.get("amsgrad") or kw.get("maximize") or kw.get("differentiable"):
+            return False
+        if tuple(self.agent.obs.shape[1:]) != (self._spec.dims[0],) or \
+                tuple(self.agent.target.shape[1:]) != (self._spec.dims[-1],):
+            return False
+        hooks = ("_sample_policy", "_calculate_grad", "_calculate_returns", "_after_optimize",
+                 "_get_policy")
+        return not any(self._hook_overridden(h) for h in hooks)
+
+    # ------------------------------------------------------------------ reference API
+    def terminate(self):
+        """Stop training after the current generation (estorch.py:150-152)."""
+        self._stop = True
+
+    def log(self):
+        """Called after every optimisation step; override to interact with
+        training (estorch.py:154-172).  Reads below synchronise with the GPU."""
+        print(f'Step: {self.step}')
+        print(f'Episode Reward: {self.episode_reward}')
+        print(f'Max Population Reward: {np.max(self.population_returns)}')
+        print(f'Max Reward: {self.best_reward}')
+
+    # -- lazily synchronised attributes (documented at estorch.py:108-117) --
+    def _slot_state(self):
+        key = ("state", id(self._active), self.step, self._gen_token)
+        if self._host_cache.get("key") != key:
+            self._host_cache = {"key": key, "state": read_state(self._active.state)}
+        return self._host_cache["state"]
+
+    _gen_token = 0
+
+    @property
+    def episode_reward(self):
+        if "_episode_reward" in self.__dict__:
+            return self.__dict__["_episode_reward"]
+        return self._slot_state()["episode_reward"]
+
+    @episode_reward.setter
+    def episode_reward(self, value):
+        self.__dict__["_episode_reward"] = value
+
+    @property
+    def best_reward(self):
+        if "_best_reward" in self.__dict__:
+            return self.__dict__["_best_reward"]
+        if self._fused and self._active is not None:
+            return self._slot_state()["best_reward"]
+        return -float("inf")
+
+    @best_reward.setter
+    def best_reward(self, value):
+        self.__dict__["_best_reward"] = value
+
+    @property
+    def best_policy_dict(self):
+        if "_best_policy_dict" in self.__dict__:
+            return self.__dict__["_best_policy_dict"]
+        slot = self._best_slot if getattr(self, "_best_slot", None) is not None else self._active
+        if slot is None or self.best_reward == -float("inf"):
+            raise AttributeError("best_policy_dict is set after the first improving generation")
+        out, idx = OrderedDict(), 0
+        flat = slot.best_theta.detach().clone()
+        names = [k for k, _ in slot.module.named_parameters()]
+        sd = slot.module.state_dict()
+        for k in sd:
+            if k in names:
+                sz = sd[k].numel()
+                out[k] = flat[idx: idx + sz].view(sd[k].shape).clone()
+                idx += sz
+            else:
+                out[k] = sd[k].detach().clone()
+        return out
+
+    @best_policy_dict.setter
+    def best_policy_dict(self, value):
+        self.__dict__["_best_policy_dict"] = value
+
+    @property
+    def population_returns(self):
+        """np.float32 ``[P, 1]`` (ES) or ``[P, 2]`` = (reward, novelty) (NS family,
+        estorch.py:441)."""
+        if "_population_returns" in self.__dict__:
+            return self.__dict__["_population_returns"]
+        cols = [self._returns] if self._novelty is None else [self._returns, self._novelty]
+        return torch.stack(cols, dim=1).cpu().numpy()
+
+    @population_returns.setter
+    def population_returns(self, value):
+        self.__dict__["_population_returns"] = value
+
+    # ------------------------------------------------------------------ hooks (estorch.py:174-205)
+    @_builtin
+    def _get_policy(self):
+        return self.policy, self.optimizer
+
+    @_builtin
+    def _sample_policy(self, policy):
+        """-> (population_parameters, epsilon), both lazy ``[P, n]`` handles
+        (estorch.py:187-193)."""
+        slot = self._slot_of(policy)
+        slot.push_theta()
+        slot.theta_prev.copy_(slot.theta)
+        self._draw_offsets()
+        args = (self._be, slot.theta_prev, self._table, self._offsets_all, self.sigma, self.population_size)
+        return LazyPopulation(*args), NoiseHandle(*args)
+
+    @_builtin
+    def _calculate_returns(self, parameters):
+        """Host rollouts over parameter rows (estorch.py:195-202)."""
+        returns = []
+        for parameter in parameters:
+            torch.nn.utils.vector_to_parameters(parameter.to(self.device), self.target.parameters())
+            returns.append(self.agent.rollout(self.target))
+        return np.array(returns, dtype=np.float32)[:, np.newaxis]
+
+    @_builtin
+    def _calculate_grad(self, epsilon):
+        """Flat gradient estimate ``(c @ eps) / (P*sigma)`` (estorch.py:174-179)."""
+        return self._grad_from(epsilon, self.population_returns[:, 0], None, 1.0, 0.0)
+
+    @_builtin
+    def _after_optimize(self, policy):
+        self.episode_reward = self.agent.rollout(policy)             # estorch.py:182
+        if self.episode_reward > self.best_reward:
+            self.best_reward = self.episode_reward
+            self.best_policy_dict = copy.deepcopy(policy.state_dict())
+
+    # ------------------------------------------------------------------ device helpers
+    def _slot_of(self, policy):
+        for s in self._slots:
+            if s.module is policy:
+                return s
+        raise ValueError("policy is not managed by this ES instance")
+
+    def _draw_offsets(self):
+        be = self._be
+        gen = self.step
+        be.make_offsets(self._noise_seed, None, gen, self._pair_begin, self._pairs_local,
+                        self._table.numel(), self.n_parameters, self._offsets, self._order)
+        if self.n_workers > 1:
+            be.make_offsets(self._noise_seed, None, gen, 0, self._pairs, self._table.numel(),
+                            self.n_parameters, self._offsets_all, None)
+
+    def _grad_from(self, epsilon, rewards, novelty, w_rew, w_nov):
+        """Gradient estimate for the hooks path: device reduction when ``epsilon``
+        is the engine's NoiseHandle, dense matmul when a subclass supplied its
+        own tensor."""
+        P = self.population_size
+        if not isinstance(epsilon, NoiseHandle):
+            c = torch.from_numpy(rank_transformation(rewards)).float()
+            if novelty is not None:
+                c_nov = torch.from_numpy(rank_transformation(novelty)).float()
+                c = w_rew * c + w_nov * c_nov
+            eps = epsilon.to(torch.float32)
+            return (torch.mm(c.unsqueeze(0).to(eps.device), eps) / (P * self.sigma)).squeeze()
+        be = self._be
+        self._returns.copy_(torch.as_tensor(np.ascontiguousarray(rewards, dtype=np.float32)))
+        nov = None
+        if novelty is not None:
+            self._ensure_novelty()
+            self._novelty.copy_(torch.as_tensor(np.ascontiguousarray(novelty, dtype=np.float32)))
+            nov = self._novelty
+        gsum = self._grad
+        be.rank_grad(self._returns, nov, w_rew, w_nov, P, self._table, self._offsets, self._order,
+                     self._pair_begin, self._pairs_local, self.n_parameters, gsum, self._ranks, self._ranks2)
+        self._all_reduce(gsum)
+        return gsum / float(P)
+
+    def _ensure_novelty(self):
+        if self._novelty is None:
+            self._novelty = self._be.zeros(self.population_size)
+            self._ranks2 = self._be.zeros(self.population_size, dtype=torch.int32)
+
+    def _all_reduce(self, t):
+        if self.n_workers > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t)
+
+    def _all_gather_halves(self, t):
+        """Every rank wrote its local pairs' +/- members into ``t``; complete it
+        (replaces the master's Recv loop, estorch.py:228-233)."""
+        if self.n_workers == 1:
+            return
+        import torch.distributed as dist
+        pl, pb, pairs = self._pairs_local, self._pair_begin, self._pairs
+        dist.all_gather_into_tensor(t[:pairs], t[pb: pb + pl].clone())
+        dist.all_gather_into_tensor(t[pairs:], t[pairs + pb: pairs + pb + pl].clone())
+
+    def _ensure_dist(self):
+        if self.n_workers > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                backend = "nccl" if self._dev.type == "cuda" else "gloo"
+                dist.init_process_group(backend=backend)
+
+    # ------------------------------------------------------------------ fused generation
+    def _adam_desc(self, optimizer):
+        g = optimizer.param_groups[0]
+        return adam_desc(lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], clamp=1.0)
+
+    def _upload_batch(self):
+        nb = self.agent.next_batch(self.step)
+        if nb is not None:
+            obs, tgt = nb
+            self._obs.copy_(obs, non_blocking=True)
+            self._tgt.copy_(tgt, non_blocking=True)
+
+    def _fused_generation(self, slot):
+        """One generation, entirely on the device (no host synchronisation)."""
+        be, P, pairs, pl, pb = self._be, self.population_size, self._pairs, self._pairs_local, self._pair_begin
+        dims = self._spec.dims
+        self._upload_batch()
+        slot.theta_prev.copy_(slot.theta)
+        self._draw_offsets()
+        R = self._returns
+        be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
+                    self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl])
+        self._all_gather_halves(R)
+        ad = self._adam_desc(slot.optimizer)
+        if self.n_workers == 1:
+            be.rank_grad_adam(R, None, 1.0, 0.0, P, self._table, self._offsets, self._order,
+                              slot.theta, slot.m, slot.v, slot.state, ad, self._ranks, None, self._grad)
+        else:
+            be.rank_grad(R, None, 1.0, 0.0, P, self._table, self._offsets, self._order, pb, pl,
+                         self.n_parameters, self._grad, self._ranks, None)
+            self._all_reduce(self._grad)
+            be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
+        be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode)
+        be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
+        self._best_slot = slot
+
+    @property
+    def population_parameters(self):
+        """Lazy ``[P, n]`` view of the last sampled population (estorch.py:216)."""
+        if "_population_parameters" in self.__dict__:
+            return self.__dict__["_population_parameters"]
+        slot = self._active
+        return LazyPopulation(self._be, slot.theta_prev, self._table, self._offsets_all, self.sigma,
+                              self.population_size)
+
+    @population_parameters.setter
+    def population_parameters(self, value):
+        self.__dict__["_population_parameters"] = value
+
+    # ------------------------------------------------------------------ hooks-mode generation
+    def _hooks_generation(self):
+        """The reference's control flow (estorch.py:215-246) through its hooks."""
+        policy, optimizer = self._get_policy()
+        self.population_parameters, epsilon = self._sample_policy(policy)
+        per = self.population_size // self.n_workers
+        pop = self.population_parameters
+        if isinstance(pop, LazyPopulation):
+            # a rank owns pairs, i.e. the matching +/- rows (estorch.py:217-223 sends
+            # contiguous row blocks instead; the set of evaluated members is the same)
+            pl, pb, pairs = self._pairs_local, self._pair_begin, self._pairs
+            plus = self._calculate_returns(pop.rows(pb, pl))
+            minus = self._calculate_returns(pop.rows(pairs + pb, pl))
+            width = plus.shape[1]
+            full = np.empty((self.population_size, width), dtype=np.float32)
+            full[pb: pb + pl], full[pairs + pb: pairs + pb + pl] = plus, minus
+            if self.n_workers > 1:
+                t = torch.from_numpy(full).to(self._dev)
+                for c in range(width):
+                    col = t[:, c].contiguous()
+                    self._all_gather_halves(col)
+                    t[:, c] = col
+                full = t.cpu().numpy()
+            self.population_returns = full
+        else:
+            start = self.rank * per
+            returns = self._calculate_returns(pop[start: start + per])
+            if self.n_workers > 1:
+                import torch.distributed as dist
+                parts = [None] * self.n_workers
+                dist.all_gather_object(parts, returns)
+                returns = np.concatenate(parts)
+            self.population_returns = returns
+        grad = self._calculate_grad(epsilon)
+        index = 0
+        for parameter in policy.parameters():                         # estorch.py:236-244
+            size = int(np.prod(parameter.shape))
+            parameter.grad = (-grad[index:index + size].view(parameter.shape).to(parameter.device))
+            parameter.grad.data.clamp_(-1.0, 1.0)
+            index += size
+        optimizer.step()                                              # estorch.py:245
+        self._after_optimize(policy)
+
+    # ------------------------------------------------------------------ main loop
+    def _master(self):
+        """Generation loop (estorch.py:211-250).  Every rank runs it; only rank 0
+        calls ``log`` (the reference's workers have no log either)."""
+        self.step = 0
+        self._ensure_dist()
+        for s in self._slots:
+            s.ensure_flat()
+        with torch.no_grad():
+            while self.step < self.n_steps and not self._stop:
+                self._gen_token += 1
+                if self._fused:
+                    for k in ("_episode_reward", "_best_reward", "_best_policy_dict",
+                              "_population_returns", "_population_parameters"):
+                        self.__dict__.pop(k, None)
+                    self._active = self._select_slot()
+                    self._fused_generation(self._active)
+                else:
+                    self._hooks_generation()
+                if (self.step + 1) % self._log_interval == 0:
+                    if self.rank == 0:
+                        self.log()
+                    self._sync_stop()
+                self.step += 1
+        if self._fused:
+            for s in self._slots:
+                s.mirror_adam_state()
+            torch.cuda.synchronize(self._dev) if self._dev.type == "cuda" else None
+
+    def _select_slot(self):
+        return self._slots[0]
+
+    def _sync_stop(self):
+        """Rank 0's ``terminate()`` must stop every rank at the same generation."""
+        if self.n_workers > 1:
+            import torch.distributed as dist
+            flag = torch.tensor([1.0 if self._stop else 0.0], device=self._dev)
+            dist.broadcast(flag, src=0)
+            self._stop = bool(flag.item() > 0)
+
+    def train(self, n_steps, n_proc=1, hwthread=False, hostfile=None):
+        """Train for ``n_steps`` generations (estorch.py:272-308).
+
+        ``n_proc`` is the number of GPUs (one process per GPU).  Like the
+        reference, which re-executes the calling script under ``mpirun``
+        (estorch.py:41-56,:305), a single-process call with ``n_proc > 1``
+        re-executes the script under ``torch.distributed.run`` and exits; when
+        already running under a launcher (``WORLD_SIZE`` set) it just trains.
+        ``hwthread`` is accepted and ignored; ``hostfile`` (multi-node MPI) is
+        not supported.
+        """
+        self.n_steps = n_steps
+        if hostfile is not None:
+            raise NotImplementedError("hostfile (multi-node MPI launch) has no B200 single-box equivalent")
+        if n_proc > 1:
+            if self._trained:
+                raise RuntimeError("train function can not be called more than once.")
+            self._trained = True
+            if self.n_workers == 1:
+                from .launch import fork_under_torchrun
+                if fork_under_torchrun(n_proc):
+                    sys.exit(0)
+            elif self.n_workers != n_proc:
+                raise RuntimeError(f"train(n_proc={n_proc}) but the launcher started {self.n_workers} processes")
+        self._master()
+
+
+class NS_ES(ES):
+    """Novelty Search ES (Conti et al. 2018) -- reference estorch.py:311-472.
+    Maintains a meta-population of ``meta_population_size`` (policy, optimizer)
+    pairs and an archive of behaviour characteristics; the gradient follows
+    novelty only.  ``population_returns`` is ``[P, 2]`` = (reward, novelty)."""
+
+    _ALGORITHM_TYPE = _Algorithm.novelty
+    _W_REW, _W_NOV = 0.0, 1.0
+
+    def __init__(self, policy, agent, optimizer, population_size, sigma=0.01,
+                 meta_population_size=3, k=10, device=torch.device("cpu"),
+                 policy_kwargs={}, agent_kwargs={}, optimizer_kwargs={}, **engine_kwargs):
+        super().__init__(policy, agent, optimizer, population_size, sigma, device,
+                         policy_kwargs, agent_kwargs, optimizer_kwargs, **engine_kwargs)
+        self.meta_population_size = meta_population_size
+        self.k = k
+        self._archive = []
+        self.meta_population = []
+        self._ensure_novelty()
+        if self._fused:
+            bc_dim = self.agent.bc_dim
+            if not bc_dim:
+                raise ValueError("NS-family device agents need bc_obs / bc_dim")
+            self._bc = self._be.zeros(self.population_size, bc_dim)
+            self._bc_center = self._be.zeros(1, bc_dim)
+            self._nov_center = self._be.zeros(1)
+        for _ in range(self.meta_population_size):                    # estorch.py:401-408
+            p = self._make_module()
+            optim = optimizer(p.parameters(), **optimizer_kwargs)
+            self.meta_population.append((p, optim))
+            self._slots.append(_PolicySlot(p, optim, self._be, self._fused))
+            reward, bc = self._rollout_bc(p)
+            if bc is None:
+                raise ValueError("Behaviour Charateristics is None")
+            self._archive.append(bc)
+        self._active = self._slots[0]
+        self._best_host = -float("inf")
+
+    def _rollout_bc(self, policy):
+        """Initial archive entry of a meta-population member (estorch.py:405)."""
+        if self._fused:
+            slot = self._slots[-1]
+            self._be.eval_mlp_center(self._spec.dims, slot.theta, self._obs, self._tgt, self._episode,
+                                     self._bc_center[0], self.agent.bc_obs, self.agent.bc_dim)
+            return float(self._episode.item()), self._bc_center[0].cpu().numpy().copy()
+        with torch.no_grad():
+            return self.agent.rollout(policy)
+
+    # -- host novelty (estorch.py:412-417), brute force in float64
+    @_builtin
+    def _calculate_novelty(self, bc, _archive):
+        a = np.asarray(_archive, dtype=np.float64)
+        d = np.sqrt(((a - np.asarray(bc, dtype=np.float64)[None, :]) ** 2).sum(axis=1))
+        d.sort()
+        return np.sum(d[:self.k]) / np.linalg.norm(a)
+
+    @_builtin
+    def _calculate_grad(self, epsilon):
+        r = self.population_returns
+        return self._grad_from(epsilon, r[:, 0], r[:, 1], np.float32(self._w_rew()), np.float32(self._w_nov()))
+
+    def _w_rew(self):
+        return self._W_REW
+
+    def _w_nov(self):
+        return self._W_NOV
+
+    @_builtin
+    def _after_optimize(self, policy):
+        self.episode_reward, bc = self.agent.rollout(policy)          # estorch.py:427-432
+        self._archive.append(bc)
+        if self.episode_reward > self.best_reward:
+            self.best_reward = self.episode_reward
+            self.best_policy_dict = copy.deepcopy(policy.state_dict())
+
+    @_builtin
+    def _calculate_returns(self, parameters):
+        returns = []
+        for parameter in parameters:                                  # estorch.py:434-442
+            torch.nn.utils.vector_to_parameters(parameter.to(self.device), self.target.parameters())
+            reward, bc = self.agent.rollout(self.target)
+            returns.append((reward, self._calculate_novelty(bc, self._archive)))
+        return np.array(returns, dtype=np.float32)
+
+    @_builtin
+    def _get_policy(self):
+        total_novelty = []                                            # estorch.py:444-456
+        for policy, _ in self.meta_population:
+            reward, bc = self.agent.rollout(policy)
+            total_novelty.append(self._calculate_novelty(bc, self._archive))
+        total_novelty = np.array(total_novelty)
+        probability = total_novelty / np.sum(total_novelty)
+        self.idx = np.random.choice(np.arange(len(self.meta_population), dtype=int), p=probability)
+        self._active = self._slots[self.idx]
+        return self.meta_population[self.idx]
+
+    # ------------------------------------------------------------------ fused NS generation
+    def _archive_tensor(self):
+        return torch.from_numpy(np.ascontiguousarray(np.stack(self._archive), dtype=np.float32)).to(self._dev)
+
+    def _select_slot(self):
+        """Device version of ``_get_policy``: M centre rollouts + kNN novelty,
+        then the reference's ``np.random.choice`` on the host (estorch.py:451-454)."""
+        be, dims = self._be, self._spec.dims
+        arch = self._archive_tensor()
+        nov = []
+        for s in self._slots:
+            be.eval_mlp_center(dims, s.theta, self._obs, self._tgt, self._episode, self._bc_center[0],
+                               self.agent.bc_obs, self.agent.bc_dim)
+            be.knn_novelty(self._bc_center, arch, self.k, self._nov_center)
+            nov.append(self._nov_center.clone())
+        total = torch.cat(nov).double().cpu().numpy()
+        self.idx = np.random.choice(np.arange(len(self.meta_population), dtype=int), p=total / np.sum(total))
+        if self.n_workers > 1:                      # every rank must pick the same policy
+            import torch.distributed as dist
+            t = torch.tensor([self.idx], device=self._dev)
+            dist.broadcast(t, src=0)
+            self.idx = int(t.item())
+        self._arch_dev = arch
+        return self._slots[self.idx]
+
+    def _fused_generation(self, slot):
+        be, P, pairs, pl, pb = self._be, self.population_size, self._pairs, self._pairs_local, self._pair_begin
+        dims, ag = self._spec.dims, self.agent
+        self._upload_batch()
+        slot.theta_prev.copy_(slot.theta)
+        self._draw_offsets()
+        R, N, BC = self._returns, self._novelty, self._bc
+        be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
+                    self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
+                    BC[pb: pb + pl], BC[pairs + pb: pairs + pb + pl], ag.bc_obs, ag.bc_dim)
+        be.knn_novelty(BC[pb: pb + pl], self._arch_dev, self.k, N[pb: pb + pl])
+        be.knn_novelty(BC[pairs + pb: pairs + pb + pl], self._arch_dev, self.k, N[pairs + pb: pairs + pb + pl])
+        self._all_gather_halves(R)
+        self._all_gather_halves(N)
+        ad = self._adam_desc(slot.optimizer)
+        w_rew, w_nov = np.float32(self._w_rew()), np.float32(self._w_nov())
+        if self.n_workers == 1:
+            be.rank_grad_adam(R, N, w_rew, w_nov, P, self._table, self._offsets, self._order,
+                              slot.theta, slot.m, slot.v, slot.state, ad, self._ranks, self._ranks2, self._grad)
+        else:
+            be.rank_grad(R, N, w_rew, w_nov, P, self._table, self._offsets, self._order, pb, pl,
+                         self.n_parameters, self._grad, self._ranks, self._ranks2)
+            self._all_reduce(self._grad)
+            be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
+        # _after_optimize (estorch.py:427-432 / :650-662): rollout of the updated
+        # policy, archive append, best tracking, NSRA schedule (host scalars)
+        be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, self._bc_center[0],
+                           ag.bc_obs, ag.bc_dim)
+        episode = float(self._episode.item())
+        self._archive.append(self._bc_center[0].cpu().numpy().copy())
+        self.episode_reward = episode
+        improved = episode > self._best_host
+        if improved:
+            self._best_host = episode
+            slot.best_theta.copy_(slot.theta)
+            self._best_slot = slot
+        self.best_reward = self._best_host
+        self._on_after_optimize(improved)
+
+    def _on_after_optimize(self, improved):
+        pass
+
+
+class NSR_ES(NS_ES):
+    """NSR-ES: average of reward and novelty centred ranks (estorch.py:475-549)."""
+    _W_REW, _W_NOV = 0.5, 0.5
+
+
+class NSRA_ES(NS_ES):
+    """NSRA-ES: adaptive blend ``w*c(reward) + (1-w)*c(novelty)`` with the
+    weight schedule of estorch.py:650-662.  As in the reference (estorch.py:637)
+    ``weight_delta`` is fixed at 0.05 regardless of the constructor argument."""
+
+    def __init__(self, policy, agent, optimizer, population_size, sigma=0.01,
+                 meta_population_size=3, k=10, min_weight=0.0, weight_t=50,
+                 weight_delta=0.05, device=torch.device("cpu"),
+                 policy_kwargs={}, agent_kwargs={}, optimizer_kwargs={}, **engine_kwargs):
+        super().__init__(policy=policy, agent=agent, optimizer=optimizer,
+                         population_size=population_size, sigma=sigma,
+                         meta_population_size=meta_population_size, k=k, device=device,
+                         policy_kwargs=policy_kwargs, agent_kwargs=agent_kwargs,
+                         optimizer_kwargs=optimizer_kwargs, **engine_kwargs)
+        self.weight = 1.0
+        self.min_weight = min_weight
+        self.weight_t = weight_t
+        self.weight_delta = 0.05                                      # estorch.py:637
+        self.t = 0
+
+    def _w_rew(self):
+        return self.weight
+
+    def _w_nov(self):
+        return 1.0 - self.weight
+
+    def _schedule(self, improved):
+        if improved:                                                  # estorch.py:653-657
+            self.weight = min(self.weight + self.weight_delta, 1.0)
+            self.t = 0
+        else:                                                         # :658-662
+            self.t += 1
+            if self.t >= self.weight_t:
+                self.weight = max(self.weight - self.weight_delta, self.min_weight)
+                self.t = 0
+
+    @_builtin
+    def _after_optimize(self, policy):
+        self.episode_reward, bc = self.agent.rollout(policy)
+        self._archive.append(bc)
+        improved = self.episode_reward > self.best_reward
+        if improved:
+            self.best_reward = self.episode_reward
+            self.best_policy_dict = copy.deepcopy(policy.state_dict())
+        self._schedule(improved)
+
+    def _on_after_optimize(self, improved):
+        self._schedule(improved)

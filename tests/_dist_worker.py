@@ -1,0 +1,63 @@
+"""Worker for tests/test_dist_cpu.py: one rank of a world_size-N gloo job running
+the fused ES host logic with the oracle stand-in backend.  Writes its final theta."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from _oracle_backend import OracleBackend  # noqa: E402
+import estorch_b200 as E  # noqa: E402
+from test_api_cpu import MLP, _load_theta  # noqa: E402
+
+
+def main():
+    out_dir, algo = sys.argv[1], sys.argv[2]
+    g = np.load(os.path.join(ROOT, "tests", "golden",
+                             "es_cartpole_p64.npz" if algo == "es" else "nsra_bipedal_p32.npz"))
+    dims = [int(d) for d in g["dims"]]
+    obs, tgt = torch.from_numpy(g["obs"]), torch.from_numpy(g["target"])
+    seen = []
+
+    if algo == "es":
+        class R(E.ES):
+            def log(self):
+                seen.append(self.population_returns.copy())
+                if self.step == 1:
+                    self.terminate()       # must stop EVERY rank after generation 1
+        es = R(MLP, E.DeviceAgent, torch.optim.Adam, population_size=64, sigma=0.1,
+               policy_kwargs={"dims": dims}, agent_kwargs=dict(obs=obs, target=tgt),
+               optimizer_kwargs={"lr": 0.01}, noise_table_size=len(g["table"]),
+               noise_seed=int(g["noise_seed"]), _backend=OracleBackend())
+        es._table.copy_(torch.from_numpy(g["table"]))
+        _load_theta(es.policy, g["theta0"])
+        es.train(n_steps=5)
+        theta = torch.nn.utils.parameters_to_vector(es.policy.parameters()).detach().numpy()
+    else:
+        class R(E.NSRA_ES):
+            def log(self):
+                seen.append(self.population_returns.copy())
+        np.random.seed(123)
+        es = R(MLP, E.DeviceAgent, torch.optim.Adam, population_size=32, sigma=0.02, weight_t=2,
+               policy_kwargs={"dims": dims}, agent_kwargs=dict(obs=obs, target=tgt, bc_obs=64, bc_dim=256),
+               optimizer_kwargs={"lr": 0.01}, noise_table_size=len(g["table"]),
+               noise_seed=int(g["noise_seed"]), _backend=OracleBackend())
+        es._table.copy_(torch.from_numpy(g["table"]))
+        for i, (p, _) in enumerate(es.meta_population):
+            _load_theta(p, g["meta_theta0"][i])
+        es._archive = [a.copy() for a in g["archive0"]]
+        np.random.seed(123)
+        es.train(n_steps=2)
+        theta = np.stack([torch.nn.utils.parameters_to_vector(p.parameters()).detach().numpy()
+                          for p, _ in es.meta_population])
+    np.savez(os.path.join(out_dir, f"rank{es.rank}.npz"), theta=theta, step=es.step,
+             n_logs=len(seen), returns=es.population_returns, world=es.n_workers,
+             pairs_local=es._pairs_local, pair_begin=es._pair_begin)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,56 @@
+"""Multi-process path (one process per GPU in production) exercised with
+world_size=2 over gloo on CPU: pair sharding, all-gather of returns, all-reduce
+of the partial gradient, rank-0-only logging and terminate() propagation."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(world, algo, tmp_path):
+    port = _free_port()
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_dist_worker.py"),
+                                       str(tmp_path), algo], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    return [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+
+
+def test_world2_es_sharded_generation(tmp_path):
+    g = load_golden("es_cartpole_p64.npz")
+    r0, r1 = _run(2, "es", tmp_path)
+    assert int(r0["world"]) == 2 and int(r0["pairs_local"]) == 16
+    assert int(r0["pair_begin"]) == 0 and int(r1["pair_begin"]) == 16
+    # terminate() on rank 0 at step 1 stopped both ranks after 2 generations
+    assert int(r0["step"]) == 2 and int(r1["step"]) == 2
+    assert int(r0["n_logs"]) == 2 and int(r1["n_logs"]) == 0         # only rank 0 logs
+    np.testing.assert_array_equal(r0["theta"], r1["theta"])            # replicas stay bit-identical
+    np.testing.assert_array_equal(r0["returns"], r1["returns"])
+    assert rel_err(r0["returns"][:, 0], g["returns"][1][:, 0]) < 1e-5
+    assert rel_err(r0["theta"], g["theta_after"][1]) < 1e-4
+
+
+def test_world2_nsra_sharded_generation(tmp_path):
+    g = load_golden("nsra_bipedal_p32.npz")
+    r0, r1 = _run(2, "nsra", tmp_path)
+    np.testing.assert_array_equal(r0["theta"], r1["theta"])
+    assert rel_err(r0["returns"][:, 1], g["returns"][1][:, 1]) < 1e-4

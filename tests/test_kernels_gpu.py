@@ -319,7 +319,8 @@ def test_full_size_north_star_gradient_property(be):
     assert float((g - want).abs().max() / want.abs().max()) < 1e-5
     assert float((out[-1.0][0] + g).abs().max() / g.abs().max()) < 1e-6
     # first Adam step from zero state moves every parameter by ~lr*sign(-g)
-    ok = g.abs() > 1e-4 * g.abs().max()
+    # (|g| >> Adam eps=1e-8, so m/(sqrt(v)+eps) is +-1 to 1e-4)
+    ok = g.abs() > 1e-2 * g.abs().max()
     assert float((th[ok] + 0.01 * torch.sign(-g[ok])).abs().max()) < 1e-5
 
 
