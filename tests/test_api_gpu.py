@@ -143,7 +143,9 @@ def test_north_star_shape_one_generation_properties():
     before = es._slots[0].theta.clone()
     es.train(n_steps=1)
     ret = es.population_returns[:, 0]
-    assert np.isfinite(ret).all() and len(np.unique(ret)) == 4096
+    # (fp32 returns DO tie at this scale -- ~30k representable values around -1.0 for
+    #  4096 members -- so the stable-by-index tie rule is exercised here)
+    assert np.isfinite(ret).all() and len(np.unique(ret)) > 2048
     ranks = es._ranks.cpu().numpy()
     np.testing.assert_array_equal(np.sort(ranks), np.arange(4096))
     np.testing.assert_array_equal(ranks, orc.compute_ranks(ret))
