@@ -260,7 +260,8 @@ def run_ours(args, wl, rank, world, local_rank):
     R = es._returns
     t_eval = timed(lambda: be.eval_mlp(es._spec.dims, slot.theta, es._table, es._offsets, es._order, pl, sigma,
                                        es._obs, es._tgt, R[es._pair_begin: es._pair_begin + pl],
-                                       R[pairs + es._pair_begin: pairs + es._pair_begin + pl]), iters=3)
+                                       R[pairs + es._pair_begin: pairs + es._pair_begin + pl],
+                                       precision=es._precision), iters=3)
     scratch = [t.clone() for t in (slot.theta, slot.m, slot.v)]
     ad = adam_desc(lr=0.01)
     if world == 1:
@@ -279,7 +280,7 @@ def run_ours(args, wl, rank, world, local_rank):
               "algorithmic_bytes": bytes_grad,
               "note": "frac > 1 is L2 reuse: table rows of one generation overlap and pairs are reduced in "
                       "offset-sorted order, so most bytes are served by L2, not HBM"}
-    k_eval = {"kernel": "eval_mlp", "bound": "tensor", "achieved": flops_eval / t_eval / 1e9,
+    k_eval = {"kernel": "eval_mlp_" + es._precision, "bound": "tensor", "achieved": flops_eval / t_eval / 1e9,
               "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": flops_eval / t_eval / 1e9 / peaks["tensor"],
               "ms": t_eval, "traffic": None, "algorithmic_bytes": bytes_eval, "flops": flops_eval,
               "hbm_frac_of_noise_stream": bytes_eval / t_eval / 1e6 / peaks["hbm"]}
@@ -298,8 +299,10 @@ def run_ours(args, wl, rank, world, local_rank):
     line = {"metric": "generations/sec at pop=4096, 1M-param MLP", "value": args.steps / (ms / 1e3),
             "unit": "generations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, wl, world),
+            "vs_baseline": None,
+            "dtype": "bf16 operands / f32 accumulate (evaluate GEMMs); f32 noise, ranks, reduction, Adam"
+                     if es._precision == "bf16" else "f32",
+            "data": "synthetic", "config": workload_config(args, wl, world),
             "e2e": {"value": args.steps / e2e_s, "unit": "generations/s",
                     "h2d_bytes_per_step": int(obs.numel() * 4 + tgt.numel() * 4),
                     "d2h_bytes_per_step": int(4 * P + 32)},
@@ -317,6 +320,7 @@ def main():
     ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
     ap.add_argument("--table-log2", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-precision", default="auto", choices=["auto", "fp32", "bf16"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -143,12 +143,17 @@ class CudaBackend:
         self.launches += 1
 
     # ---------------------------------------------------------------- evaluate
-    def eval_mlp(self, dims, theta, table, offsets, order, pairs, sigma, obs, target,
-                 ret_plus, ret_minus, bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0):
+    def eval_supports_bf16(self, dims, B) -> bool:
         d = mlp_desc(dims)
+        return bool(self.lib.estk_eval_mlp_bf16_supported(C.byref(d), int(B)))
+
+    def eval_mlp(self, dims, theta, table, offsets, order, pairs, sigma, obs, target,
+                 ret_plus, ret_minus, bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32"):
+        d = mlp_desc(dims)
+        fn = self.lib.estk_eval_mlp_bf16 if precision == "bf16" else self.lib.estk_eval_mlp
         if obs.shape != (obs.shape[0], dims[0]) or target.shape != (obs.shape[0], dims[-1]):
             raise ValueError(f"obs {tuple(obs.shape)} / target {tuple(target.shape)} do not match dims {list(dims)}")
-        _capi.check(self.lib.estk_eval_mlp(
+        _capi.check(fn(
             self._ctx, C.byref(d), self._ptr(theta, torch.float32, "theta"),
             self._ptr(table, torch.float32, "table"), self._ptr(offsets, torch.int64, "offsets"),
             self._ptr(order, torch.int32, "order"), int(pairs), float(sigma),
@@ -156,12 +161,14 @@ class CudaBackend:
             int(obs.shape[0]), self._ptr(ret_plus, torch.float32, "ret_plus"),
             self._ptr(ret_minus, torch.float32, "ret_minus"),
             self._ptr(bc_plus, torch.float32, "bc_plus"), self._ptr(bc_minus, torch.float32, "bc_minus"),
-            int(bc_obs), int(bc_dim), self._stream()), "estk_eval_mlp")
+            int(bc_obs), int(bc_dim), self._stream()), "estk_eval_mlp[" + precision + "]")
         self.launches += 1
 
-    def eval_mlp_center(self, dims, theta, obs, target, ret_out, bc_out=None, bc_obs=0, bc_dim=0):
+    def eval_mlp_center(self, dims, theta, obs, target, ret_out, bc_out=None, bc_obs=0, bc_dim=0,
+                        precision="fp32"):
         d = mlp_desc(dims)
-        _capi.check(self.lib.estk_eval_mlp_center(
+        fn = self.lib.estk_eval_mlp_center_bf16 if precision == "bf16" else self.lib.estk_eval_mlp_center
+        _capi.check(fn(
             self._ctx, C.byref(d), self._ptr(theta, torch.float32, "theta"),
             self._ptr(obs, torch.float32, "obs"), self._ptr(target, torch.float32, "target"),
             int(obs.shape[0]), self._ptr(ret_out, torch.float32, "ret_out"),

@@ -1,0 +1,548 @@
+// estk_eval_mlp_tc.cu -- kernel 1 of the ES generation on the 5th-gen tensor
+// cores (tcgen05 + TMEM), bf16 operands / fp32 accumulation.
+//
+// Same contract as estk_eval_mlp (estk_eval_mlp.cu; reference estorch.py:187-202 +
+// Policy.forward examples/cartpole_es.py:14-20 + synthetic agent of SURVEY 8d),
+// for policies whose dense layers are worth a GEMM.
+//
+// Work unit ("task") = (antithetic pair j, sign s, chunk of 128*CG observations),
+// executed by a cluster of CG CTAs (CG = 2: one tcgen05.mma.cta_group::2 pair,
+// UMMA M = 256).  Per layer  D[obs, out] = H[obs, in] * W_s[out, in]^T :
+//   A operand  activations H, 128 observation rows per CTA, bf16, K-major,
+//              128B-swizzled, RESIDENT in shared memory across layers (in place);
+//   B operand  W_s = theta + s*sigma*eps, formed ON THE FLY by the producer
+//              warps (128-bit loads of theta (L2) and of the pair's noise row,
+//              one FMA, cvt.rn.bf16x2, 16-byte swizzled st.shared) into a ring
+//              of [N/CG x 64] tiles -- the perturbed weights never exist in
+//              global memory; each CTA of the pair forms its half of N;
+//   D          the WHOLE layer output [128 x <=512] fp32 lives in TMEM (512
+//              columns); the epilogue warps read it back (tcgen05.ld), add the
+//              perturbed bias, apply ReLU, round to bf16 and overwrite H; the
+//              last layer is fused with the squared-error reduction instead.
+// Warp roles per CTA: w0 MMA issuer (leader CTA only), w1 TMEM allocator,
+// w2-5 epilogue (TMEM lane quarter = warp % 4), w6-9 weight producers.
+// Pipelines: full/empty mbarriers on the B ring, acc_full (layer accumulated),
+// h_ready (next layer's activations in place).  Persistent: clusters loop over
+// tasks; the two signs of a pair run on neighbouring clusters at the same time,
+// so the second read of the noise row is an L2 hit.
+//
+// Roofline: 2*n*B*2*pairs flops per launch on the tensor pipe; the noise stream
+// 4*n*pairs bytes is read once from HBM (second sign from L2).
+#include "estk_common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int kMaxW = 512;            // max layer width (K and N) of this path
+constexpr int kBlockK = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int kKBlockBytes = 128 * kBlockK * 2;   // one [128 x 64] bf16 tile = 16 KB
+constexpr int kStageBytes = kKBlockBytes;         // B ring stage (<= 128 rows per CTA at CG=2)
+constexpr int kNumEpiWarps = 4, kNumProdWarps = 4;
+constexpr int kThreadsTC = 32 * (2 + kNumEpiWarps + kNumProdWarps);   // 320
+
+struct EvalTCParams {
+  estk_mlp_desc desc;
+  const float* theta;
+  const float* table;
+  const int64_t* offsets;  // null => centre evaluation
+  const int32_t* order;
+  int pairs;
+  float sigma;
+  const float* obs;
+  const float* target;
+  int B, chunks;           // chunks of 128*CG observations
+  float* ret_plus;
+  float* ret_minus;
+  float* bc_plus;
+  float* bc_minus;
+  int bc_obs, bc_dim;
+  float* partial;          // [pairs*2][chunks*CG]
+  unsigned int* counters;  // [pairs*2]
+  int n_tasks;             // pairs * n_signs * chunks
+  int n_signs;             // 2, or 1 for the centre evaluation
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+template <int CG>
+__device__ __forceinline__ void mbar_arrive_on(uint32_t bar, uint32_t cta) {
+  if constexpr (CG == 1) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}" ::"r"(bar), "r"(cta) : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
+        "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
+        "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+// all previously issued MMAs complete -> arrive (once) on `bar` in every CTA of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+//  version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64)).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
+// K-major A and B, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of the 16-byte chunk (row r, chunk c8 of 8 bf16) inside a swizzled [rows x 64] tile
+__device__ __forceinline__ uint32_t sw128_offset(int r, int c8) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+struct Layer { int K, N; int64_t wbase, bbase; };
+
+template <int CG>
+__global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTCParams p) {
+  constexpr int kStages = (CG == 2) ? 4 : 2;
+  constexpr int kStageB = (CG == 2) ? kStageBytes : 2 * kStageBytes;   // up to 256 rows at CG=1
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sH = smem;                                    // 8 k-blocks x 16 KB
+  uint8_t* sB = sH + (kMaxW / kBlockK) * kKBlockBytes;   // ring
+  float* sBias = reinterpret_cast<float*>(sB + kStages * kStageB);   // [2][512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * kMaxW);
+  uint64_t* bar_full = bars;                 // [kStages]  (leader's are used)
+  uint64_t* bar_empty = bars + kStages;      // [kStages]  (local)
+  uint64_t* bar_acc = bars + 2 * kStages;    // layer accumulated (local)
+  uint64_t* bar_h = bars + 2 * kStages + 1;  // activations in place (leader's is used)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kNumEpiWarps]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CG, n_clusters = gridDim.x / CG;
+  const int L = p.desc.n_layers;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(bar_full + s), CG * kNumProdWarps);
+      mbar_init(smem_u32(bar_empty + s), 1);
+    }
+    mbar_init(smem_u32(bar_acc), 1);
+    mbar_init(smem_u32(bar_h), CG * kNumEpiWarps);
+    fence_barrier_init();
+  }
+  if (CG == 2) cluster_sync_all();
+  if (warp == 1) tmem_alloc<CG>(smem_u32(s_tmem), 512);
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+
+  // per-layer geometry (tiny; every role recomputes it)
+  Layer lay[ESTK_MAX_LAYERS];
+  {
+    int64_t pb = 0;
+    for (int l = 0; l < L; ++l) {
+      lay[l].K = p.desc.dims[l];
+      lay[l].N = p.desc.dims[l + 1];
+      lay[l].wbase = pb;
+      lay[l].bbase = pb + (int64_t)lay[l].K * lay[l].N;
+      pb = lay[l].bbase + lay[l].N;
+    }
+  }
+  const bool centre = (p.offsets == nullptr);
+
+  if (warp == 0) {
+    // =================================================================== MMA issuer
+    if (cta_rank == 0) {
+      uint32_t stage = 0, ring_phase = 0, h_phase = 0;
+      for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
+        for (int l = 0; l < L; ++l) {
+          mbar_wait(smem_u32(bar_h), h_phase);
+          h_phase ^= 1;
+          tc_fence_after();
+          const int K = lay[l].K, N = lay[l].N;
+          for (int n0 = 0; n0 < N; n0 += 256) {
+            const int Ng = min(256, N - n0);
+            const uint32_t idesc = make_idesc(128 * CG, Ng);
+            const uint32_t tmem_d = tmem_base + (uint32_t)n0;
+            for (int kb = 0; kb < K / kBlockK; ++kb) {
+              mbar_wait(smem_u32(bar_full + stage), ring_phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a_addr = smem_u32(sH + kb * kKBlockBytes);
+                const uint32_t b_addr = smem_u32(sB + stage * kStageB);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t da = make_sw128_desc(a_addr + k * 32);
+                  const uint64_t db = make_sw128_desc(b_addr + k * 32);
+                  umma_bf16<CG>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit<CG>(smem_u32(bar_empty + stage));          // frees the ring slot (both CTAs)
+                if (n0 + 256 >= N && kb == K / kBlockK - 1) umma_commit<CG>(smem_u32(bar_acc));
+              }
+              __syncwarp();
+              if (++stage == kStages) { stage = 0; ring_phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 2 + kNumEpiWarps) {
+    // =================================================================== epilogue warps
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;             // observation row inside the CTA's 128
+    const int etid = (warp - 2) * 32 + lane;   // 0..127
+    uint32_t acc_phase = 0;
+    for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
+      const int chunk = task % p.chunks;
+      const int sgn = (task / p.chunks) % p.n_signs;
+      const int slot = task / (p.chunks * p.n_signs);
+      const int j = p.order ? p.order[slot] : slot;
+      const float* trow = centre ? p.theta : p.table + p.offsets[j];
+      const float ssig = centre ? 0.f : (sgn ? -p.sigma : p.sigma);
+      const int b = (chunk * CG + (int)cta_rank) * 128 + row;      // global observation index
+      // ---- stage this CTA's observations as the layer-0 A operand
+      {
+        const int K0 = lay[0].K;
+        const float* orow = p.obs + (size_t)b * K0;
+        for (int c = 0; c < K0 / 8; ++c) {
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(orow + c * 8));
+          const float4 x1 = __ldg(reinterpret_cast<const float4*>(orow + c * 8 + 4));
+          const uint32_t addr = smem_u32(sH + (c >> 3) * kKBlockBytes) + sw128_offset(row, c & 7);
+          st_shared_v4(addr, pack_bf16(x0.x, x0.y), pack_bf16(x0.z, x0.w), pack_bf16(x1.x, x1.y), pack_bf16(x1.z, x1.w));
+        }
+      }
+      float loss = 0.f;
+      for (int l = 0; l < L; ++l) {
+        const int N = lay[l].N;
+        float* bias = sBias + (l & 1) * kMaxW;
+        for (int o = etid; o < N; o += 32 * kNumEpiWarps)
+          bias[o] = fmaf(ssig, ld_noise1(trow + lay[l].bbase + o), __ldg(p.theta + lay[l].bbase + o));
+        // H (and, for l > 0, the previous layer's TMEM reads) are done: release the MMA warp
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar_sync(1, 32 * kNumEpiWarps);   // also publishes bias[] among the epilogue warps
+        if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h), 0);
+        // ---- wait for the layer's accumulators
+        mbar_wait(smem_u32(bar_acc), acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const bool last = (l == L - 1);
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          if (!last) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {      // 4 chunks of 8 output features = 16 bytes of bf16
+              float y[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + bias[c0 + g * 8 + e], 0.f);
+              const int col = c0 + g * 8;
+              const uint32_t addr = smem_u32(sH + (col >> 6) * kKBlockBytes) + sw128_offset(row, (col & 63) >> 3);
+              st_shared_v4(addr, pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+            }
+          } else {
+            const float* trg = p.target + (size_t)b * N + c0;
+            float* bc = sgn ? p.bc_minus : p.bc_plus;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(trg + g * 4));
+              const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int o = c0 + g * 4 + e;
+                const float y = __uint_as_float(v[g * 4 + e]) + bias[o];
+                const float d = y - tv[e];
+                loss = fmaf(d, d, loss);
+                if (bc) {
+                  const int64_t idx = (int64_t)b * N + o;
+                  if (b < p.bc_obs && idx < p.bc_dim) bc[(size_t)j * p.bc_dim + idx] = y;
+                }
+              }
+            }
+          }
+        }
+      }
+      // ---- squared-error partial of this CTA; the last arriver combines them in fixed order
+      loss = warp_sum_f(loss);
+      if (lane == 0) s_loss[warp - 2] = loss;
+      named_bar_sync(2, 32 * kNumEpiWarps);
+      if (etid == 0) {
+        const float tot = (s_loss[0] + s_loss[1]) + (s_loss[2] + s_loss[3]);
+        const int parts = p.chunks * CG;
+        const int cell = slot * 2 + sgn;
+        float* part = p.partial + (size_t)cell * parts;
+        part[chunk * CG + (int)cta_rank] = tot;
+        __threadfence();
+        const unsigned int arrived = atomicAdd(p.counters + cell, 1u);
+        if (arrived == (unsigned int)parts - 1) {
+          __threadfence();
+          float s = 0.f;
+          for (int c = 0; c < parts; ++c) s += __ldcg(part + c);
+          const float r = -(s / ((float)p.B * (float)lay[L - 1].N));
+          if (sgn) p.ret_minus[j] = r; else p.ret_plus[j] = r;
+          p.counters[cell] = 0u;
+        }
+      }
+      named_bar_sync(2, 32 * kNumEpiWarps);   // s_loss reusable
+    }
+  } else if (warp >= 2 + kNumEpiWarps) {
+    // =================================================================== weight producers
+    const int ptid = (warp - 2 - kNumEpiWarps) * 32 + lane;   // 0..127
+    uint32_t stage = 0, ring_phase = 0;
+    for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
+      const int sgn = (task / p.chunks) % p.n_signs;
+      const int slot = task / (p.chunks * p.n_signs);
+      const int j = p.order ? p.order[slot] : slot;
+      const float* trow = centre ? p.theta : p.table + p.offsets[j];
+      const float ssig = centre ? 0.f : (sgn ? -p.sigma : p.sigma);
+      for (int l = 0; l < L; ++l) {
+        const int K = lay[l].K, N = lay[l].N;
+        for (int n0 = 0; n0 < N; n0 += 256) {
+          const int Ng = min(256, N - n0);
+          const int rows = Ng / CG;                               // this CTA's share of the B tile
+          const int64_t rbase = lay[l].wbase + (int64_t)(n0 + (int)cta_rank * rows) * K;
+          for (int kb = 0; kb < K / kBlockK; ++kb) {
+            mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
+            const uint32_t sbase = smem_u32(sB + stage * kStageB);
+            const int n_items = rows * 8;                          // 16-byte output chunks
+            for (int it0 = 0; it0 < n_items; it0 += 128 * 4) {
+              float4 th[4][2], ep[4][2];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * 128 + ptid;
+                if (it < n_items) {
+                  const int64_t idx = rbase + (int64_t)(it >> 3) * K + kb * kBlockK + (it & 7) * 8;
+                  th[u][0] = __ldg(reinterpret_cast<const float4*>(p.theta + idx));
+                  th[u][1] = __ldg(reinterpret_cast<const float4*>(p.theta + idx + 4));
+                  ep[u][0] = ld_noise4(reinterpret_cast<const float4*>(trow + idx));
+                  ep[u][1] = ld_noise4(reinterpret_cast<const float4*>(trow + idx + 4));
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * 128 + ptid;
+                if (it < n_items) {
+                  const uint32_t w0 = pack_bf16(fmaf(ssig, ep[u][0].x, th[u][0].x), fmaf(ssig, ep[u][0].y, th[u][0].y));
+                  const uint32_t w1 = pack_bf16(fmaf(ssig, ep[u][0].z, th[u][0].z), fmaf(ssig, ep[u][0].w, th[u][0].w));
+                  const uint32_t w2 = pack_bf16(fmaf(ssig, ep[u][1].x, th[u][1].x), fmaf(ssig, ep[u][1].y, th[u][1].y));
+                  const uint32_t w3 = pack_bf16(fmaf(ssig, ep[u][1].z, th[u][1].z), fmaf(ssig, ep[u][1].w, th[u][1].w));
+                  st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
+                }
+              }
+            }
+            fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_full + stage), 0);
+            if (++stage == kStages) { stage = 0; ring_phase ^= 1; }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+template <int CG>
+size_t tc_smem_bytes() {
+  const int stages = (CG == 2) ? 4 : 2;
+  const int stage_b = (CG == 2) ? kStageBytes : 2 * kStageBytes;
+  return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)stages * stage_b + 2 * kMaxW * sizeof(float) +
+         (2 * stages + 2) * sizeof(uint64_t) + 64;
+}
+
+template <int CG>
+int launch_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream) {
+  const size_t smem = tc_smem_bytes<CG>();
+  ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int clusters = ctx->sm_count / CG;
+  if (clusters > p.n_tasks) clusters = p.n_tasks;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kThreadsTC);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_tc_kernel<CG>, p));
+  return ESTK_OK;
+}
+
+int tc_supported(const estk_mlp_desc& d, int B, int cg, const char** why) {
+  if (d.n_layers < 1 || d.n_layers > ESTK_MAX_LAYERS) { *why = "n_layers"; return 0; }
+  if (d.activation != 0) { *why = "activation"; return 0; }
+  for (int l = 0; l < d.n_layers; ++l) {
+    if (d.dims[l] % 64 || d.dims[l] > kMaxW || d.dims[l] < 64) { *why = "layer input width must be a multiple of 64 in [64,512]"; return 0; }
+    const int N = d.dims[l + 1];
+    if (N % 32 || N > kMaxW || N < 32) { *why = "layer output width must be a multiple of 32 in [32,512]"; return 0; }
+  }
+  if (B % (128 * cg)) { *why = "batch must be a multiple of 256"; return 0; }
+  return 1;
+}
+
+int run_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream, const char* who) {
+  const char* why = "";
+  const int cg = 2;
+  if (!tc_supported(p.desc, p.B, cg, &why)) {
+    estk_set_error("%s: shape not supported by the tcgen05 path (%s)", who, why);
+    return ESTK_ERR_UNSUPPORTED;
+  }
+  ESTK_CHECK_ARG(p.pairs >= 1 && p.pairs <= ESTK_MAX_POPULATION / 2, "%s: pairs=%d", who, p.pairs);
+  p.chunks = p.B / (128 * cg);
+  ESTK_CHECK_ARG(p.chunks * cg <= kEvalMaxChunks, "%s: batch too large", who);
+  p.n_tasks = p.pairs * p.n_signs * p.chunks;
+  p.partial = ctx->eval_partial;
+  p.counters = ctx->counters;
+  return launch_tc<2>(ctx, p, stream);
+}
+
+}  // namespace
+
+extern "C" int estk_eval_mlp_bf16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                                  const float* table, const int64_t* offsets, const int32_t* order,
+                                  int32_t pairs, float sigma, const float* obs, const float* target,
+                                  int32_t B, float* returns_plus, float* returns_minus, float* bc_plus,
+                                  float* bc_minus, int32_t bc_obs, int32_t bc_dim, void* stream) {
+  ESTK_CHECK_ARG(ctx && desc && theta && table && offsets && obs && target && returns_plus && returns_minus,
+                 "estk_eval_mlp_bf16: null argument");
+  ESTK_CHECK_ARG((bc_plus == nullptr) == (bc_minus == nullptr), "estk_eval_mlp_bf16: bc_plus/bc_minus must both be set or both null");
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(table) && ESTK_ALIGNED16(obs) && ESTK_ALIGNED16(target),
+                 "estk_eval_mlp_bf16: theta/table/obs/target must be 16-byte aligned");
+  EvalTCParams p = {};
+  p.desc = *desc; p.theta = theta; p.table = table; p.offsets = offsets; p.order = order;
+  p.pairs = pairs; p.sigma = sigma; p.obs = obs; p.target = target; p.B = B;
+  p.ret_plus = returns_plus; p.ret_minus = returns_minus;
+  p.bc_plus = bc_plus; p.bc_minus = bc_minus; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
+  p.n_signs = 2;
+  return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_bf16");
+}
+
+extern "C" int estk_eval_mlp_center_bf16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                                         const float* obs, const float* target, int32_t B,
+                                         float* return_out, float* bc_out, int32_t bc_obs,
+                                         int32_t bc_dim, void* stream) {
+  ESTK_CHECK_ARG(ctx && desc && theta && obs && target && return_out, "estk_eval_mlp_center_bf16: null argument");
+  EvalTCParams p = {};
+  p.desc = *desc; p.theta = theta; p.table = theta; p.offsets = nullptr; p.order = nullptr;
+  p.pairs = 1; p.sigma = 0.f; p.obs = obs; p.target = target; p.B = B;
+  p.ret_plus = return_out; p.ret_minus = nullptr;
+  p.bc_plus = bc_out; p.bc_minus = nullptr; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
+  p.n_signs = 1;
+  return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_center_bf16");
+}
+
+extern "C" int estk_eval_mlp_bf16_supported(const estk_mlp_desc* desc, int32_t B) {
+  const char* why = "";
+  return desc ? tc_supported(*desc, B, 2, &why) : 0;
+}

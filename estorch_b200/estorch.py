@@ -165,6 +165,9 @@ class ES:
         noise_seed: seed of the table and of the per-generation offsets.
         log_interval: call ``log()`` every k-th generation only (default 1 =
             reference behaviour).
+        eval_precision: arithmetic of the fused evaluate kernel: ``"fp32"`` (exact
+            CUDA-core path), ``"bf16"`` (tcgen05 tensor cores, bf16 operands, fp32
+            accumulation) or ``"auto"`` (bf16 when the policy shape supports it).
     Attributes as documented at estorch.py:108-117.
     """
 
@@ -173,7 +176,7 @@ class ES:
     def __init__(self, policy, agent, optimizer, population_size, sigma=0.01,
                  device=torch.device("cpu"), policy_kwargs={}, agent_kwargs={},
                  optimizer_kwargs={}, *, noise_table_size=None, noise_seed=42,
-                 log_interval=1, _backend=None):
+                 log_interval=1, eval_precision="auto", _backend=None):
         self.rank, self.n_workers, self._local_rank = _dist_env()
         self.population_size = int(population_size)
         assert not (self.population_size % self.n_workers)           # estorch.py:130
@@ -204,6 +207,16 @@ class ES:
         self._spec = mlp_spec_from_module(self.target)
         self._fused = self._decide_fused(optimizer)
         self._host_cache = {}
+        if eval_precision not in ("auto", "fp32", "bf16"):
+            raise ValueError("eval_precision must be 'auto', 'fp32' or 'bf16'")
+        self._precision = "fp32"
+        if self._fused and eval_precision != "fp32":
+            supported = getattr(self._be, "eval_supports_bf16", lambda d, b: False)(
+                self._spec.dims, self.agent.obs.shape[0])
+            if eval_precision == "bf16" and not supported:
+                raise ValueError("eval_precision='bf16' needs layer widths that are multiples of 64 (in) / "
+                                 "32 (out), at most 512, and a batch that is a multiple of 256")
+            self._precision = "bf16" if supported else "fp32"
 
         # ---- noise table (replicated on every GPU, identical by construction)
         n_pad = (self.n_parameters + 31) // 32 * 32
@@ -470,7 +483,8 @@ class ES:
         self._draw_offsets()
         R = self._returns
         be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
-                    self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl])
+                    self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
+                    precision=self._precision)
         self._all_gather_halves(R)
         ad = self._adam_desc(slot.optimizer)
         if self.n_workers == 1:
@@ -481,7 +495,7 @@ class ES:
                          self.n_parameters, self._grad, self._ranks, None)
             self._all_reduce(self._grad)
             be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
-        be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode)
+        be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, precision=self._precision)
         be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
         self._best_slot = slot
 
@@ -651,7 +665,8 @@ class NS_ES(ES):
         if self._fused:
             slot = self._slots[-1]
             self._be.eval_mlp_center(self._spec.dims, slot.theta, self._obs, self._tgt, self._episode,
-                                     self._bc_center[0], self.agent.bc_obs, self.agent.bc_dim)
+                                     self._bc_center[0], self.agent.bc_obs, self.agent.bc_dim,
+                                     precision=self._precision)
             return float(self._episode.item()), self._bc_center[0].cpu().numpy().copy()
         with torch.no_grad():
             return self.agent.rollout(policy)
@@ -716,7 +731,7 @@ class NS_ES(ES):
         nov = []
         for s in self._slots:
             be.eval_mlp_center(dims, s.theta, self._obs, self._tgt, self._episode, self._bc_center[0],
-                               self.agent.bc_obs, self.agent.bc_dim)
+                               self.agent.bc_obs, self.agent.bc_dim, precision=self._precision)
             be.knn_novelty(self._bc_center, arch, self.k, self._nov_center)
             nov.append(self._nov_center.clone())
         total = torch.cat(nov).double().cpu().numpy()
@@ -738,7 +753,8 @@ class NS_ES(ES):
         R, N, BC = self._returns, self._novelty, self._bc
         be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
                     self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
-                    BC[pb: pb + pl], BC[pairs + pb: pairs + pb + pl], ag.bc_obs, ag.bc_dim)
+                    BC[pb: pb + pl], BC[pairs + pb: pairs + pb + pl], ag.bc_obs, ag.bc_dim,
+                    precision=self._precision)
         be.knn_novelty(BC[pb: pb + pl], self._arch_dev, self.k, N[pb: pb + pl])
         be.knn_novelty(BC[pairs + pb: pairs + pb + pl], self._arch_dev, self.k, N[pairs + pb: pairs + pb + pl])
         self._all_gather_halves(R)
@@ -756,7 +772,7 @@ class NS_ES(ES):
         # _after_optimize (estorch.py:427-432 / :650-662): rollout of the updated
         # policy, archive append, best tracking, NSRA schedule (host scalars)
         be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, self._bc_center[0],
-                           ag.bc_obs, ag.bc_dim)
+                           ag.bc_obs, ag.bc_dim, precision=self._precision)
         episode = float(self._episode.item())
         self._archive.append(self._bc_center[0].cpu().numpy().copy())
         self.episode_reward = episode

@@ -130,6 +130,25 @@ ESTK_API int estk_eval_mlp(estk_ctx* ctx, const estk_mlp_desc* desc, const float
                   float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim,
                   void* stream);
 
+/* Tensor-core variant of estk_eval_mlp: same contract, bf16 operands with fp32
+ * accumulation on tcgen05 (weights theta+-sigma*eps are rounded to bf16 when the
+ * B-operand tile is formed, activations when they are written back).  Shapes:
+ * every layer input width a multiple of 64 in [64,512], every output width a
+ * multiple of 32 in [32,512], B a multiple of 256; otherwise
+ * ESTK_ERR_UNSUPPORTED (estk_eval_mlp_bf16_supported() tells in advance).
+ * Returns agree with the fp32 path to ~1e-2 relative (stated in the tests). */
+ESTK_API int estk_eval_mlp_bf16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                       const float* table, const int64_t* offsets, const int32_t* order,
+                       int32_t pairs, float sigma, const float* obs, const float* target, int32_t B,
+                       float* returns_plus, float* returns_minus,
+                       float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim,
+                       void* stream);
+ESTK_API int estk_eval_mlp_center_bf16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                              const float* obs, const float* target, int32_t B,
+                              float* return_out, float* bc_out, int32_t bc_obs, int32_t bc_dim,
+                              void* stream);
+ESTK_API int estk_eval_mlp_bf16_supported(const estk_mlp_desc* desc, int32_t B);
+
 /* Unperturbed policy (estorch.py:181-182 `_after_optimize` rollout):
  * return_out[0] = return of theta; bc_out (nullable) [bc_dim]. */
 ESTK_API int estk_eval_mlp_center(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,

@@ -31,7 +31,7 @@ import numpy as np
 __all__ = [
     "compute_ranks", "center_values", "rank_transformation",
     "mix64", "noise_slots", "noise_offsets", "philox4x32_10", "philox_normal_table",
-    "mlp_param_count", "mlp_unflatten", "mlp_forward", "synthetic_return", "synthetic_bc",
+    "mlp_param_count", "mlp_unflatten", "mlp_forward", "mlp_forward_bf16", "round_bf16", "synthetic_return", "synthetic_bc",
     "sample_population", "evaluate_population",
     "blend_weights", "calculate_grad", "calculate_grad_pairs", "negate_clamp",
     "adam_step", "novelty", "nsra_weight_update", "vbn_stats", "vbn_normalize",
@@ -185,6 +185,28 @@ def mlp_forward(flat: np.ndarray, dims: Sequence[int], obs: np.ndarray) -> np.nd
         h = (h @ w.T + b).astype(np.float32)
         if li + 1 < len(layers):
             h = np.maximum(h, np.float32(0.0))
+    return h
+
+
+def round_bf16(x: np.ndarray) -> np.ndarray:
+    """fp32 -> bf16 (round to nearest even) -> fp32, like cvt.rn.bf16.f32."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    u = (u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)
+    return u.view(np.float32)
+
+
+def mlp_forward_bf16(flat: np.ndarray, dims: Sequence[int], obs: np.ndarray) -> np.ndarray:
+    """Numerics of the tcgen05 evaluate path (estk_eval_mlp_bf16): weights and
+    layer inputs rounded to bf16, products accumulated in fp32, bias / ReLU in
+    fp32.  ``flat`` is the already-perturbed fp32 row."""
+    h = round_bf16(np.asarray(obs, dtype=np.float32))
+    layers = mlp_unflatten(np.asarray(flat, dtype=np.float32), dims)
+    for li, (w, b) in enumerate(layers):
+        z = (h.astype(np.float64) @ round_bf16(w).astype(np.float64).T).astype(np.float32) + b
+        if li + 1 < len(layers):
+            h = round_bf16(np.maximum(z, np.float32(0.0)))
+        else:
+            h = z.astype(np.float32)
     return h
 
 

@@ -348,3 +348,49 @@ def test_track_best(be):
         assert s["episode_reward"] == r
     assert read_state(st)["best_reward"] == -1.0
     assert float(best.min()) == 3.0 and float(best.max()) == 3.0
+
+
+# ------------------------------------------------------------------ tcgen05 evaluate (bf16 operands)
+@pytest.mark.parametrize("dims,B,pairs,bc", [([128, 512, 512, 288], 256, 5, 0), ([64, 64, 32], 256, 3, 0),
+                                             ([128, 512, 512, 512, 512, 288], 256, 3, 0),
+                                             ([64, 256, 64], 512, 4, 256), ([192, 320, 96], 256, 2, 0)])
+def test_eval_mlp_bf16_tensor_core_path(be, dims, B, pairs, bc):
+    """bf16-operand / fp32-accumulate tcgen05 path: within 5e-4 (max-norm relative) of the
+    oracle that emulates its roundings, and within 2e-2 of the exact fp32 forward."""
+    rng = np.random.RandomState(7)
+    n = orc.mlp_param_count(dims)
+    assert be.eval_supports_bf16(dims, B)
+    table_len = (n + 31) // 32 * 32 + (1 << 14)
+    table = rng.standard_normal(table_len).astype(np.float32)
+    theta = np.concatenate([np.concatenate([(rng.uniform(-1, 1, dims[i] * dims[i + 1]) / np.sqrt(dims[i])),
+                                            rng.uniform(-1, 1, dims[i + 1]) / np.sqrt(dims[i])])
+                            for i in range(len(dims) - 1)]).astype(np.float32)
+    obs = rng.standard_normal((B, dims[0])).astype(np.float32)
+    tgt = rng.standard_normal((B, dims[-1])).astype(np.float32)
+    offs = orc.noise_offsets(11, 0, 0, pairs, table_len, n)
+    order = np.argsort(offs, kind="stable").astype(np.int32)
+    ret = be.zeros(2 * pairs)
+    bcp = be.zeros(pairs, bc) if bc else None
+    bcm = be.zeros(pairs, bc) if bc else None
+    be.eval_mlp(dims, dev(be, theta), dev(be, table), dev(be, offs), dev(be, order), pairs, 0.02, dev(be, obs),
+                dev(be, tgt), ret[:pairs], ret[pairs:], bcp, bcm, 64 if bc else 0, bc, precision="bf16")
+    torch.cuda.synchronize()
+    got = ret.cpu().numpy()
+    pop, _ = orc.sample_population(theta, table, offs, 0.02)
+    outs = [orc.mlp_forward_bf16(pop[i], dims, obs) for i in range(2 * pairs)]
+    emu = np.array([orc.synthetic_return(o, tgt) for o in outs], dtype=np.float32)
+    exact, _ = orc.evaluate_population(pop, dims, obs, tgt)
+    assert rel_err(got, emu) < 5e-4
+    assert rel_err(got, exact) < 2e-2
+    if bc:
+        want_bc = np.stack([orc.synthetic_bc(o, 64, bc) for o in outs])
+        got_bc = np.concatenate([bcp.cpu().numpy(), bcm.cpu().numpy()])
+        assert np.max(np.abs(got_bc - want_bc)) < 5e-3 * np.max(np.abs(want_bc))
+    one = be.zeros(1)
+    be.eval_mlp_center(dims, dev(be, theta), dev(be, obs), dev(be, tgt), one, precision="bf16")
+    want = float(orc.synthetic_return(orc.mlp_forward_bf16(theta, dims, obs), tgt))
+    assert abs(float(one) - want) < 5e-4 * abs(want)
+    # unsupported shapes are refused, not silently rerouted
+    with pytest.raises(RuntimeError, match="not supported"):
+        be.eval_mlp([4, 64, 2], dev(be, theta[:450]), dev(be, table), dev(be, offs), None, pairs, 0.02,
+                    dev(be, obs[:, :4].copy()), dev(be, tgt[:, :2].copy()), ret[:pairs], ret[pairs:], precision="bf16")
