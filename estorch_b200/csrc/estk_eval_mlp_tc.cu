@@ -20,7 +20,7 @@
 //              perturbed bias, apply ReLU, round to bf16 and overwrite H; the
 //              last layer is fused with the squared-error reduction instead.
 // Warp roles per CTA: w0 MMA issuer (leader CTA only), w1 TMEM allocator,
-// w2-5 epilogue (TMEM lane quarter = warp % 4), w6-9 weight producers.
+// w2-5 epilogue (TMEM lane quarter = warp % 4), w6-13 weight producers (2 groups of 4).
 // Pipelines: full/empty mbarriers on the B ring, acc_full (layer accumulated),
 // h_ready (next layer's activations in place).  Persistent: clusters loop over
 // tasks; the two signs of a pair run on neighbouring clusters at the same time,
@@ -30,6 +30,9 @@
 // 4*n*pairs bytes is read once from HBM (second sign from L2).
 #include "estk_common.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
+
+__device__ unsigned long long g_tc_prof[32];   // ESTK_TC_DEBUG bit 8: per-role cycle counters of cluster 0 / CTA 0
 
 namespace {
 
@@ -37,7 +40,8 @@ constexpr int kMaxW = 512;            // max layer width (K and N) of this path
 constexpr int kBlockK = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int kKBlockBytes = 128 * kBlockK * 2;   // one [128 x 64] bf16 tile = 16 KB
 constexpr int kStageBytes = kKBlockBytes;         // B ring stage (<= 128 rows per CTA at CG=2)
-constexpr int kNumEpiWarps = 4, kNumProdWarps = 4;
+constexpr int kNumEpiWarps = 4, kNumProdWarps = 8;
+constexpr int kProdGroups = 2, kProdGroupWarps = kNumProdWarps / kProdGroups;   // groups work on different ring stages concurrently
 constexpr int kThreadsTC = 32 * (2 + kNumEpiWarps + kNumProdWarps);   // 320
 
 struct EvalTCParams {
@@ -60,6 +64,7 @@ struct EvalTCParams {
   unsigned int* counters;  // [pairs*2]
   int n_tasks;             // pairs * n_signs * chunks
   int n_signs;             // 2, or 1 for the centre evaluation
+  int dbg;                 // ESTK_TC_DEBUG bit mask (perf triage only): 1 no producer loads, 2 no epilogue work, 4 no MMA
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -77,7 +82,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// wait with CLUSTER-scope acquire: only for barriers that receive arrivals from the
+// peer CTA (full[], h_ready on the leader).  ptxas pairs a cluster-scope acquire
+// with CCTL.IVALL (L1 invalidate + drain of outstanding loads), so the producers
+// and the epilogue use the CTA-scope variant below on their local barriers.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -88,21 +97,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
 // arrive on the barrier at the same smem offset in CTA `cta` of the cluster
 template <int CG>
 __device__ __forceinline__ void mbar_arrive_on(uint32_t bar, uint32_t cta) {
   if constexpr (CG == 1) {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
   } else {
     asm volatile(
         "{\n"
         ".reg .b32 ra;\n"
         "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
         "}" ::"r"(bar), "r"(cta) : "memory");
   }
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy st.shared -> visible to the async proxy (tensor core reads of smem)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -169,8 +193,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
@@ -195,11 +219,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 struct Layer { int K, N; int64_t wbase, bbase; };
+#define PROF_ON (prof)
+#define PROF_T() (PROF_ON ? clock64() : 0ll)
+#define PROF_ADD(i, t0) do { if (PROF_ON) atomicAdd(&g_tc_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
 
 template <int CG>
 __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTCParams p) {
@@ -217,6 +249,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
   uint64_t* bar_h = bars + 2 * kStages + 1;  // activations in place (leader's is used)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
   float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kNumEpiWarps]
+  int* s_prog = reinterpret_cast<int*>(s_loss + kNumEpiWarps);   // n-groups started by the producers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -224,8 +257,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
   const int L = p.desc.n_layers;
 
   if (warp == 0 && lane == 0) {
+    *s_prog = 0;
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(bar_full + s), CG * kNumProdWarps);
+      mbar_init(smem_u32(bar_full + s), CG * kProdGroupWarps);
       mbar_init(smem_u32(bar_empty + s), 1);
     }
     mbar_init(smem_u32(bar_acc), 1);
@@ -239,9 +273,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
 
-  // per-layer geometry (tiny; every role recomputes it)
-  Layer lay[ESTK_MAX_LAYERS];
-  {
+  // per-layer geometry, in shared memory (a local-memory array would miss the L1
+  // that the weight stream keeps evicting)
+  __shared__ Layer lay[ESTK_MAX_LAYERS];
+  if (threadIdx.x == 0) {
     int64_t pb = 0;
     for (int l = 0; l < L; ++l) {
       lay[l].K = p.desc.dims[l];
@@ -251,15 +286,20 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       pb = lay[l].bbase + lay[l].N;
     }
   }
+  __syncthreads();
   const bool centre = (p.offsets == nullptr);
+  const bool prof = (p.dbg & 8) && blockIdx.x == 0 && lane == 0;
 
   if (warp == 0) {
     // =================================================================== MMA issuer
     if (cta_rank == 0) {
       uint32_t stage = 0, ring_phase = 0, h_phase = 0;
+      const long long tm0 = PROF_T();
       for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
         for (int l = 0; l < L; ++l) {
+          const long long th0 = PROF_T();
           mbar_wait(smem_u32(bar_h), h_phase);
+          PROF_ADD(1, th0);
           h_phase ^= 1;
           tc_fence_after();
           const int K = lay[l].K, N = lay[l].N;
@@ -268,13 +308,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             const uint32_t idesc = make_idesc(128 * CG, Ng);
             const uint32_t tmem_d = tmem_base + (uint32_t)n0;
             for (int kb = 0; kb < K / kBlockK; ++kb) {
+              const long long tf0 = PROF_T();
               mbar_wait(smem_u32(bar_full + stage), ring_phase);
+              PROF_ADD(2, tf0);
+              const long long ti0 = PROF_T();
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t a_addr = smem_u32(sH + kb * kKBlockBytes);
                 const uint32_t b_addr = smem_u32(sB + stage * kStageB);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
+                for (int k = 0; k < kBlockK / 16 && !(p.dbg & 4); ++k) {
                   const uint64_t da = make_sw128_desc(a_addr + k * 32);
                   const uint64_t db = make_sw128_desc(b_addr + k * 32);
                   umma_bf16<CG>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -283,11 +326,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
                 if (n0 + 256 >= N && kb == K / kBlockK - 1) umma_commit<CG>(smem_u32(bar_acc));
               }
               __syncwarp();
+              PROF_ADD(3, ti0);
               if (++stage == kStages) { stage = 0; ring_phase ^= 1; }
             }
           }
         }
       }
+      PROF_ADD(0, tm0);
     }
   } else if (warp >= 2 && warp < 2 + kNumEpiWarps) {
     // =================================================================== epilogue warps
@@ -295,7 +340,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     const int row = q * 32 + lane;             // observation row inside the CTA's 128
     const int etid = (warp - 2) * 32 + lane;   // 0..127
     uint32_t acc_phase = 0;
+    const bool eprof = prof && warp == 2;
+    const long long te0 = eprof ? clock64() : 0ll;
     for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
+      const long long to0 = eprof ? clock64() : 0ll;
       const int chunk = task % p.chunks;
       const int sgn = (task / p.chunks) % p.n_signs;
       const int slot = task / (p.chunks * p.n_signs);
@@ -307,15 +355,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       {
         const int K0 = lay[0].K;
         const float* orow = p.obs + (size_t)b * K0;
-        for (int c = 0; c < K0 / 8; ++c) {
-          const float4 x0 = __ldg(reinterpret_cast<const float4*>(orow + c * 8));
-          const float4 x1 = __ldg(reinterpret_cast<const float4*>(orow + c * 8 + 4));
-          const uint32_t addr = smem_u32(sH + (c >> 3) * kKBlockBytes) + sw128_offset(row, c & 7);
-          st_shared_v4(addr, pack_bf16(x0.x, x0.y), pack_bf16(x0.z, x0.w), pack_bf16(x1.x, x1.y), pack_bf16(x1.z, x1.w));
+        for (int c0 = 0; c0 < K0 / 8; c0 += 8) {            // 16 independent 128-bit loads per batch
+          float4 x[8][2];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            x[u][0] = __ldg(reinterpret_cast<const float4*>(orow + (c0 + u) * 8));
+            x[u][1] = __ldg(reinterpret_cast<const float4*>(orow + (c0 + u) * 8 + 4));
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u;
+            const uint32_t addr = smem_u32(sH + (c >> 3) * kKBlockBytes) + sw128_offset(row, c & 7);
+            st_shared_v4(addr, pack_bf16(x[u][0].x, x[u][0].y), pack_bf16(x[u][0].z, x[u][0].w),
+                         pack_bf16(x[u][1].x, x[u][1].y), pack_bf16(x[u][1].z, x[u][1].w));
+          }
         }
       }
+      if (eprof) atomicAdd(&g_tc_prof[11], (unsigned long long)(clock64() - to0));
       float loss = 0.f;
       for (int l = 0; l < L; ++l) {
+        const long long tb0 = eprof ? clock64() : 0ll;
         const int N = lay[l].N;
         float* bias = sBias + (l & 1) * kMaxW;
         for (int o = etid; o < N; o += 32 * kNumEpiWarps)
@@ -325,23 +384,37 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
         tc_fence_before();
         named_bar_sync(1, 32 * kNumEpiWarps);   // also publishes bias[] among the epilogue warps
         if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h), 0);
+        if (eprof) atomicAdd(&g_tc_prof[12], (unsigned long long)(clock64() - tb0));
         // ---- wait for the layer's accumulators
+        const long long ta0 = eprof ? clock64() : 0ll;
         mbar_wait(smem_u32(bar_acc), acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        if (eprof) atomicAdd(&g_tc_prof[13], (unsigned long long)(clock64() - ta0));
+        const long long tx0 = eprof ? clock64() : 0ll;
         const bool last = (l == L - 1);
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        // two 32-column TMEM loads in flight per wait
+        auto consume = [&](const uint32_t (&v)[32], int c0) {
+          float bv[32];
+          {
+            const uint32_t baddr = smem_u32(bias + c0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 t = ld_shared_v4(baddr + g * 16);
+              bv[g * 4 + 0] = t.x; bv[g * 4 + 1] = t.y; bv[g * 4 + 2] = t.z; bv[g * 4 + 3] = t.w;
+            }
+          }
           if (!last) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              pk[e] = pack_bf16(fmaxf(__uint_as_float(v[2 * e]) + bv[2 * e], 0.f),
+                                fmaxf(__uint_as_float(v[2 * e + 1]) + bv[2 * e + 1], 0.f));
 #pragma unroll
             for (int g = 0; g < 4; ++g) {      // 4 chunks of 8 output features = 16 bytes of bf16
-              float y[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) y[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + bias[c0 + g * 8 + e], 0.f);
               const int col = c0 + g * 8;
               const uint32_t addr = smem_u32(sH + (col >> 6) * kKBlockBytes) + sw128_offset(row, (col & 63) >> 3);
-              st_shared_v4(addr, pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+              st_shared_v4(addr, pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
             }
           } else {
             const float* trg = p.target + (size_t)b * N + c0;
@@ -353,7 +426,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int o = c0 + g * 4 + e;
-                const float y = __uint_as_float(v[g * 4 + e]) + bias[o];
+                const float y = __uint_as_float(v[g * 4 + e]) + bv[g * 4 + e];
                 const float d = y - tv[e];
                 loss = fmaf(d, d, loss);
                 if (bc) {
@@ -363,7 +436,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
               }
             }
           }
+        };
+        const uint32_t trow_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < N && !(p.dbg & 2); c0 += 32) {
+          uint32_t va[32];
+          const long long tl0 = eprof ? clock64() : 0ll;
+          tmem_ld32(trow_addr + (uint32_t)c0, va);
+          tmem_ld_wait();
+          if (p.dbg & 16) {            // triage: TMEM read only
+            uint32_t x = 0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x ^= va[e];
+            if (x == 0x12345u) loss += 1.f;
+            if (eprof) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - tl0));
+            continue;
+          }
+          if (eprof) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - tl0));
+          consume(va, c0);
         }
+        if (eprof) atomicAdd(&g_tc_prof[14], (unsigned long long)(clock64() - tx0));
       }
       // ---- squared-error partial of this CTA; the last arriver combines them in fixed order
       loss = warp_sum_f(loss);
@@ -388,58 +479,137 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       }
       named_bar_sync(2, 32 * kNumEpiWarps);   // s_loss reusable
     }
+    if (eprof) atomicAdd(&g_tc_prof[10], (unsigned long long)(clock64() - te0));
   } else if (warp >= 2 + kNumEpiWarps) {
     // =================================================================== weight producers
-    const int ptid = (warp - 2 - kNumEpiWarps) * 32 + lane;   // 0..127
-    uint32_t stage = 0, ring_phase = 0;
-    for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
-      const int sgn = (task / p.chunks) % p.n_signs;
-      const int slot = task / (p.chunks * p.n_signs);
-      const int j = p.order ? p.order[slot] : slot;
-      const float* trow = centre ? p.theta : p.table + p.offsets[j];
-      const float ssig = centre ? 0.f : (sgn ? -p.sigma : p.sigma);
-      for (int l = 0; l < L; ++l) {
-        const int K = lay[l].K, N = lay[l].N;
-        for (int n0 = 0; n0 < N; n0 += 256) {
-          const int Ng = min(256, N - n0);
-          const int rows = Ng / CG;                               // this CTA's share of the B tile
-          const int64_t rbase = lay[l].wbase + (int64_t)(n0 + (int)cta_rank * rows) * K;
-          for (int kb = 0; kb < K / kBlockK; ++kb) {
-            mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
-            const uint32_t sbase = smem_u32(sB + stage * kStageB);
-            const int n_items = rows * 8;                          // 16-byte output chunks
-            for (int it0 = 0; it0 < n_items; it0 += 128 * 4) {
-              float4 th[4][2], ep[4][2];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int it = it0 + u * 128 + ptid;
-                if (it < n_items) {
-                  const int64_t idx = rbase + (int64_t)(it >> 3) * K + kb * kBlockK + (it & 7) * 8;
-                  th[u][0] = __ldg(reinterpret_cast<const float4*>(p.theta + idx));
-                  th[u][1] = __ldg(reinterpret_cast<const float4*>(p.theta + idx + 4));
-                  ep[u][0] = ld_noise4(reinterpret_cast<const float4*>(trow + idx));
-                  ep[u][1] = ld_noise4(reinterpret_cast<const float4*>(trow + idx + 4));
-                }
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int it = it0 + u * 128 + ptid;
-                if (it < n_items) {
-                  const uint32_t w0 = pack_bf16(fmaf(ssig, ep[u][0].x, th[u][0].x), fmaf(ssig, ep[u][0].y, th[u][0].y));
-                  const uint32_t w1 = pack_bf16(fmaf(ssig, ep[u][0].z, th[u][0].z), fmaf(ssig, ep[u][0].w, th[u][0].w));
-                  const uint32_t w2 = pack_bf16(fmaf(ssig, ep[u][1].x, th[u][1].x), fmaf(ssig, ep[u][1].y, th[u][1].y));
-                  const uint32_t w3 = pack_bf16(fmaf(ssig, ep[u][1].z, th[u][1].z), fmaf(ssig, ep[u][1].w, th[u][1].w));
-                  st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
-                }
-              }
-            }
-            fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_full + stage), 0);
-            if (++stage == kStages) { stage = 0; ring_phase ^= 1; }
-          }
+    // Software-pipelined over the flattened (task, layer, n-group, k-block) stage
+    // sequence: while stage s is formed / stored / fenced, the 128-bit loads of
+    // stage s+1 are already in flight (item slot u is refilled as soon as it has
+    // been consumed), so L2/HBM latency overlaps the per-stage overhead.
+    // The producer warps form kProdGroups groups; group g builds stages g, g+G, g+2G, ...
+    // of the flattened sequence, so up to G stages' loads are in flight per SM and
+    // the groups' load / form / fence phases interleave.
+    const int pwarp = warp - 2 - kNumEpiWarps;
+    const int pgroup = pwarp / kProdGroupWarps;
+    const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // 0..127 inside the group
+    constexpr int kPT = 32 * kProdGroupWarps;
+    struct StageDesc { const float* th; const float* ep; int K; int n_items; float ssig; };
+    int cached_task = -1;
+    const float* cached_trow = p.theta;
+    float cached_ssig = 0.f;
+    auto setup = [&](int task, int l, int n0, int kb, StageDesc& d) {
+      if (task != cached_task) {            // two dependent global loads: once per task, not per stage
+        cached_task = task;
+        const int sgn = (task / p.chunks) % p.n_signs;
+        const int slot = task / (p.chunks * p.n_signs);
+        const int j = p.order ? p.order[slot] : slot;
+        cached_trow = centre ? p.theta : p.table + p.offsets[j];
+        cached_ssig = centre ? 0.f : (sgn ? -p.sigma : p.sigma);
+      }
+      const int K = lay[l].K;
+      const int rows = min(256, lay[l].N - n0) / CG;          // this CTA's share of the B tile
+      const int64_t rbase = lay[l].wbase + (int64_t)(n0 + (int)cta_rank * rows) * K + kb * kBlockK;
+      d.th = p.theta + rbase;
+      d.ep = cached_trow + rbase;
+      d.K = K;
+      d.n_items = rows * 8;                                    // 16-byte output chunks
+      d.ssig = cached_ssig;
+    };
+    auto advance = [&](int& task, int& l, int& n0, int& kb) -> bool {
+      if (++kb == lay[l].K / kBlockK) {
+        kb = 0;
+        n0 += 256;
+        if (n0 >= lay[l].N) {
+          n0 = 0;
+          if (++l == L) { l = 0; task += n_clusters; }
         }
       }
+      return task < p.n_tasks;
+    };
+    float4 th[4][2], ep[4][2];
+    int task = cluster_id, l = 0, n0 = 0, kb = 0;
+    bool has_cur = task < p.n_tasks;
+    for (int sk = 0; sk < pgroup && has_cur; ++sk) has_cur = advance(task, l, n0, kb);
+    StageDesc cur = {};
+    uint32_t counter = pgroup;                                // global stage index of `cur`
+    const bool pprof = prof && pwarp == 0;
+    const long long tp0 = pprof ? clock64() : 0ll;
+    while (has_cur) {
+      const uint32_t stage = counter % kStages, ring_phase = (counter / kStages) & 1u;
+      const long long ts0 = pprof ? clock64() : 0ll;
+      setup(task, l, n0, kb, cur);
+      if (pprof) atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - ts0));
+      if (kb == 0 && ptid == 0) atomicAdd(s_prog, 1);          // a new n-group starts: paces the L2 prefetcher
+      const uint32_t sbase = smem_u32(sB + stage * kStageB);
+      bool waited = false;
+      for (int it0 = 0; it0 < cur.n_items; it0 += 4 * kPT) {
+        // every 128-bit load of the batch is issued up front (16 in flight per thread) ...
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int it = it0 + u * kPT + ptid;
+          if (it < cur.n_items && !(p.dbg & 1)) {
+            const int64_t off = (int64_t)(it >> 3) * cur.K + (it & 7) * 8;
+            th[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off));
+            th[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off + 4));
+            ep[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.ep + off));
+            ep[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.ep + off + 4));
+          }
+        }
+        // ... then wait for the ring slot (almost always free already)
+        if (!waited) {
+          const long long tw0 = pprof ? clock64() : 0ll;
+          mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
+          waited = true;
+          if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
+        }
+        const long long tc0 = pprof ? clock64() : 0ll;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int it = it0 + u * kPT + ptid;
+          if (it < cur.n_items) {
+            const float sg = cur.ssig;
+            const uint32_t w0 = pack_bf16(fmaf(sg, ep[u][0].x, th[u][0].x), fmaf(sg, ep[u][0].y, th[u][0].y));
+            const uint32_t w1 = pack_bf16(fmaf(sg, ep[u][0].z, th[u][0].z), fmaf(sg, ep[u][0].w, th[u][0].w));
+            const uint32_t w2 = pack_bf16(fmaf(sg, ep[u][1].x, th[u][1].x), fmaf(sg, ep[u][1].y, th[u][1].y));
+            const uint32_t w3 = pack_bf16(fmaf(sg, ep[u][1].z, th[u][1].z), fmaf(sg, ep[u][1].w, th[u][1].w));
+            st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
+          }
+        }
+        if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
+      }
+      const long long tf0 = pprof ? clock64() : 0ll;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_full + stage), 0);
+      if (pprof) atomicAdd(&g_tc_prof[9], (unsigned long long)(clock64() - tf0));
+      for (int sk = 0; sk < kProdGroups && has_cur; ++sk) has_cur = advance(task, l, n0, kb);
+      counter += kProdGroups;
+      if (pprof) atomicAdd(&g_tc_prof[6], 1ull);
+    }
+    if (pprof) atomicAdd(&g_tc_prof[4], (unsigned long long)(clock64() - tp0));
+  } else if (warp == 1 && !centre) {
+    // =================================================================== L2 prefetcher
+    // Walks the same (task, layer, n-group) sequence one group ahead of the
+    // producers and pulls this CTA's share of the next group's noise rows
+    // (rows*K contiguous floats) from HBM into L2 with bulk prefetches, so the
+    // producers' 128-bit loads are L2 hits.  Paced by s_prog (groups started).
+    int task = cluster_id, l = 0, n0 = 0;
+    int issued = 0;
+    while (task < p.n_tasks) {
+      // wait until the producers are within one group of what has been prefetched
+      while ((int)(*reinterpret_cast<volatile int*>(s_prog)) + 1 < issued) __nanosleep(200);
+      const int slot = task / (p.chunks * p.n_signs);
+      const int j = p.order ? p.order[slot] : slot;
+      const int K = lay[l].K;
+      const int rows = min(256, lay[l].N - n0) / CG;
+      const float* src = p.table + p.offsets[j] + lay[l].wbase + (int64_t)(n0 + (int)cta_rank * rows) * K;
+      const uint32_t bytes = (uint32_t)rows * K * 4;          // multiple of 4 KB (rows % 16 == 0, K % 64 == 0)
+      const uint32_t piece = 16384;
+      for (uint32_t o = lane * piece; o < bytes; o += 32 * piece)
+        prefetch_l2_bulk(reinterpret_cast<const char*>(src) + o, min(piece, bytes - o));
+      ++issued;
+      n0 += 256;
+      if (n0 >= lay[l].N) { n0 = 0; if (++l == L) { l = 0; task += n_clusters; } }
     }
   }
 
@@ -454,7 +624,7 @@ size_t tc_smem_bytes() {
   const int stages = (CG == 2) ? 4 : 2;
   const int stage_b = (CG == 2) ? kStageBytes : 2 * kStageBytes;
   return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)stages * stage_b + 2 * kMaxW * sizeof(float) +
-         (2 * stages + 2) * sizeof(uint64_t) + 64;
+         (2 * stages + 2) * sizeof(uint64_t) + 128;
 }
 
 template <int CG>
@@ -502,6 +672,7 @@ int run_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream, const char* who)
   p.chunks = p.B / (128 * cg);
   ESTK_CHECK_ARG(p.chunks * cg <= kEvalMaxChunks, "%s: batch too large", who);
   p.n_tasks = p.pairs * p.n_signs * p.chunks;
+  { const char* e = getenv("ESTK_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.partial = ctx->eval_partial;
   p.counters = ctx->counters;
   return launch_tc<2>(ctx, p, stream);
@@ -545,4 +716,13 @@ extern "C" int estk_eval_mlp_center_bf16(estk_ctx* ctx, const estk_mlp_desc* des
 extern "C" int estk_eval_mlp_bf16_supported(const estk_mlp_desc* desc, int32_t B) {
   const char* why = "";
   return desc ? tc_supported(*desc, B, 2, &why) : 0;
+}
+
+// perf triage only (not part of estk.h): read and clear the cycle counters written when ESTK_TC_DEBUG has bit 8
+extern "C" __attribute__((visibility("default"))) int estk_debug_tc_profile(unsigned long long* host_out, int n) {
+  if (n > 32) n = 32;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(host_out, g_tc_prof, sizeof(unsigned long long) * n) != cudaSuccess) return -1;
+  unsigned long long zeros[32] = {};
+  return cudaMemcpyToSymbol(g_tc_prof, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -1;
 }

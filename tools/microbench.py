@@ -33,6 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--table-log2", type=int, default=28)
     ap.add_argument("--skip-big-eval", action="store_true")
+    ap.add_argument("--only", default="")
     args = ap.parse_args()
     be = CudaBackend(torch.device("cuda", 0))
     peak = 6569.6
@@ -44,6 +45,8 @@ def main():
     for name, dims, P, B in (("north_star_1M", [128, 512, 512, 512, 512, 288], 4096, 256),
                              ("cartpole", [4, 64, 64, 2], 4096, 256),
                              ("bipedal", [24, 64, 64, 4], 2048, 256)):
+        if args.only and name != args.only:
+            continue
         n, pairs = mlp_n(dims), P // 2
         offs = be.alloc(pairs, dtype=torch.int64)
         order = be.alloc(pairs, dtype=torch.int32)
@@ -64,17 +67,28 @@ def main():
         tgt = torch.randn(B, dims[-1], device=be.device)
         epairs = pairs
         if n > 100000:
-            if args.skip_big_eval:
-                continue
             epairs = 64
         rets = be.zeros(2 * epairs)
         for label, od in (("sorted", order if epairs == pairs else None),):
+            if n > 100000 and args.skip_big_eval:
+                continue
             med, best = timeit(lambda: be.eval_mlp(dims, theta, table, offs[:epairs].contiguous(), od, epairs, 0.02,
                                                     obs, tgt, rets[:epairs], rets[epairs:]), iters=5, warmup=2)
             flops = 2.0 * n * B * 2 * epairs
             print(json.dumps({"kernel": "eval_mlp_fp32", "config": name, "pairs": epairs, "B": B,
                               "ms_median": med, "ms_best": best, "TFLOPs": flops / med / 1e9,
                               "ms_extrapolated_full": med * pairs / epairs}), flush=True)
+        if be.eval_supports_bf16(dims, B):
+            rets2 = be.zeros(P)
+            med, best = timeit(lambda: be.eval_mlp(dims, theta, table, offs, order, pairs, 0.02, obs, tgt,
+                                                    rets2[:pairs], rets2[pairs:], precision="bf16"), iters=5, warmup=2)
+            flops = 2.0 * n * B * 2 * pairs
+            print(json.dumps({"kernel": "eval_mlp_bf16", "config": name, "pairs": pairs, "B": B, "ms_median": med,
+                              "ms_best": best, "TFLOPs": flops / med / 1e9, "frac_tensor": flops / med / 1e9 / 1431.4}),
+                  flush=True)
+            one = be.zeros(1)
+            med, best = timeit(lambda: be.eval_mlp_center(dims, theta, obs, tgt, one, precision="bf16"), iters=5, warmup=2)
+            print(json.dumps({"kernel": "eval_mlp_center_bf16", "config": name, "ms_median": med}), flush=True)
         one = be.zeros(1)
         med, best = timeit(lambda: be.eval_mlp_center(dims, theta, obs, tgt, one), iters=5, warmup=2)
         print(json.dumps({"kernel": "eval_mlp_center", "config": name, "ms_median": med}), flush=True)
