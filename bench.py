@@ -213,8 +213,8 @@ def run_ours(args, wl, rank, world, local_rank):
         return float(t.item())
 
     # ---- value: device-resident, no host sync in the loop
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~1 s to start streaming
     es.train(args.warmup)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     launches0 = be.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -314,7 +314,7 @@ def run_ours(args, wl, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
@@ -333,6 +333,9 @@ def main():
         if args.gpus > 1:
             raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} processes (WORLD_SIZE={world})")
     run_ours(args, wl, rank, world, local_rank)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -19,7 +19,9 @@
 //              columns); the epilogue warps read it back (tcgen05.ld), add the
 //              perturbed bias, apply ReLU, round to bf16 and overwrite H; the
 //              last layer is fused with the squared-error reduction instead.
-// Warp roles per CTA: w0 MMA issuer (leader CTA only), w1 TMEM allocator,
+// Warp roles per CTA: w0 MMA issuer (leader CTA only), w1 TMEM allocator (an L2
+// bulk-prefetch role for w1 was tried and removed: it raised DRAM traffic 5x by
+// evicting rows the offset-sorted order would have re-used, with no speed-up),
 // w2-5 epilogue (TMEM lane quarter = warp % 4), w6-13 weight producers (2 groups of 4).
 // Pipelines: full/empty mbarriers on the B ring, acc_full (layer accumulated),
 // h_ready (next layer's activations in place).  Persistent: clusters loop over
@@ -539,7 +541,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       const long long ts0 = pprof ? clock64() : 0ll;
       setup(task, l, n0, kb, cur);
       if (pprof) atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - ts0));
-      if (kb == 0 && ptid == 0) atomicAdd(s_prog, 1);          // a new n-group starts: paces the L2 prefetcher
       const uint32_t sbase = smem_u32(sB + stage * kStageB);
       bool waited = false;
       for (int it0 = 0; it0 < cur.n_items; it0 += 4 * kPT) {
@@ -587,30 +588,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       if (pprof) atomicAdd(&g_tc_prof[6], 1ull);
     }
     if (pprof) atomicAdd(&g_tc_prof[4], (unsigned long long)(clock64() - tp0));
-  } else if (warp == 1 && !centre) {
-    // =================================================================== L2 prefetcher
-    // Walks the same (task, layer, n-group) sequence one group ahead of the
-    // producers and pulls this CTA's share of the next group's noise rows
-    // (rows*K contiguous floats) from HBM into L2 with bulk prefetches, so the
-    // producers' 128-bit loads are L2 hits.  Paced by s_prog (groups started).
-    int task = cluster_id, l = 0, n0 = 0;
-    int issued = 0;
-    while (task < p.n_tasks) {
-      // wait until the producers are within one group of what has been prefetched
-      while ((int)(*reinterpret_cast<volatile int*>(s_prog)) + 1 < issued) __nanosleep(200);
-      const int slot = task / (p.chunks * p.n_signs);
-      const int j = p.order ? p.order[slot] : slot;
-      const int K = lay[l].K;
-      const int rows = min(256, lay[l].N - n0) / CG;
-      const float* src = p.table + p.offsets[j] + lay[l].wbase + (int64_t)(n0 + (int)cta_rank * rows) * K;
-      const uint32_t bytes = (uint32_t)rows * K * 4;          // multiple of 4 KB (rows % 16 == 0, K % 64 == 0)
-      const uint32_t piece = 16384;
-      for (uint32_t o = lane * piece; o < bytes; o += 32 * piece)
-        prefetch_l2_bulk(reinterpret_cast<const char*>(src) + o, min(piece, bytes - o));
-      ++issued;
-      n0 += 256;
-      if (n0 >= lay[l].N) { n0 = 0; if (++l == L) { l = 0; task += n_clusters; } }
-    }
   }
 
   // ---- teardown

@@ -123,7 +123,7 @@ __device__ __forceinline__ void epilogue(const RankGradParams& p, const AdamScal
 }
 
 template <int NC>
-__global__ void __launch_bounds__(kThreads, 3) rank_grad_kernel(const RankGradParams p) {
+__global__ void __launch_bounds__(kThreads) rank_grad_kernel(const RankGradParams p) {
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int lane = tid & 31;
