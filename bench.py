@@ -261,7 +261,7 @@ def run_ours(args, wl, rank, world, local_rank):
     t_eval = timed(lambda: be.eval_mlp(es._spec.dims, slot.theta, es._table, es._offsets, es._order, pl, sigma,
                                        es._obs, es._tgt, R[es._pair_begin: es._pair_begin + pl],
                                        R[pairs + es._pair_begin: pairs + es._pair_begin + pl],
-                                       precision=es._precision), iters=3)
+                                       **es._eval_kw(slot)), iters=3)
     scratch = [t.clone() for t in (slot.theta, slot.m, slot.v)]
     ad = adam_desc(lr=0.01)
     if world == 1:
@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
     ap.add_argument("--table-log2", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--eval-precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--eval-precision", default="auto", choices=["auto", "fp32", "bf16", "bf16s"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -53,6 +53,10 @@ SIGNATURES = {
                            _P, _P, _P, _P, _I32, _I32, _P],
     "estk_eval_mlp_center_bf16": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _I32, _P, _P, _I32, _I32, _P],
     "estk_eval_mlp_bf16_supported": [C.POINTER(EstkMlpDesc), _I32],
+    "estk_shadow_bf16": [_P, _P, _P, _I64, _P],
+    "estk_eval_mlp_bf16s": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _P, _P, _I32, _F32, _P, _P, _I32,
+                            _P, _P, _P, _P, _I32, _I32, _P],
+    "estk_eval_mlp_center_bf16s": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _I32, _P, _P, _I32, _I32, _P],
     "estk_track_best": [_P, _P, _P, _P, _P, _I64, _P],
     "estk_rank_grad_adam": [_P, _P, _P, _F32, _F32, _I32, _P, _P, _P, _I64, _P, _P, _P, _P,
                             C.POINTER(EstkAdamDesc), _P, _P, _P, _P],

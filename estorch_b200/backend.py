@@ -147,33 +147,54 @@ class CudaBackend:
         d = mlp_desc(dims)
         return bool(self.lib.estk_eval_mlp_bf16_supported(C.byref(d), int(B)))
 
+    def shadow_bf16(self, src, dst):
+        """dst (int16/bfloat16 storage, same numel) = bf16(src)."""
+        _capi.check(self.lib.estk_shadow_bf16(self._ctx, self._ptr(src, torch.float32, "src"),
+                                              self._ptr(dst, torch.bfloat16, "dst"), src.numel(), self._stream()),
+                    "estk_shadow_bf16")
+        self.launches += 1
+
     def eval_mlp(self, dims, theta, table, offsets, order, pairs, sigma, obs, target,
-                 ret_plus, ret_minus, bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32"):
+                 ret_plus, ret_minus, bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32",
+                 theta16=None, table16=None):
         d = mlp_desc(dims)
-        fn = self.lib.estk_eval_mlp_bf16 if precision == "bf16" else self.lib.estk_eval_mlp
         if obs.shape != (obs.shape[0], dims[0]) or target.shape != (obs.shape[0], dims[-1]):
             raise ValueError(f"obs {tuple(obs.shape)} / target {tuple(target.shape)} do not match dims {list(dims)}")
-        _capi.check(fn(
-            self._ctx, C.byref(d), self._ptr(theta, torch.float32, "theta"),
-            self._ptr(table, torch.float32, "table"), self._ptr(offsets, torch.int64, "offsets"),
-            self._ptr(order, torch.int32, "order"), int(pairs), float(sigma),
-            self._ptr(obs, torch.float32, "obs"), self._ptr(target, torch.float32, "target"),
-            int(obs.shape[0]), self._ptr(ret_plus, torch.float32, "ret_plus"),
-            self._ptr(ret_minus, torch.float32, "ret_minus"),
-            self._ptr(bc_plus, torch.float32, "bc_plus"), self._ptr(bc_minus, torch.float32, "bc_minus"),
-            int(bc_obs), int(bc_dim), self._stream()), "estk_eval_mlp[" + precision + "]")
+        common = (self._ptr(offsets, torch.int64, "offsets"), self._ptr(order, torch.int32, "order"), int(pairs),
+                  float(sigma), self._ptr(obs, torch.float32, "obs"), self._ptr(target, torch.float32, "target"),
+                  int(obs.shape[0]), self._ptr(ret_plus, torch.float32, "ret_plus"),
+                  self._ptr(ret_minus, torch.float32, "ret_minus"), self._ptr(bc_plus, torch.float32, "bc_plus"),
+                  self._ptr(bc_minus, torch.float32, "bc_minus"), int(bc_obs), int(bc_dim), self._stream())
+        th, tb = self._ptr(theta, torch.float32, "theta"), self._ptr(table, torch.float32, "table")
+        if precision == "bf16s":
+            if theta16 is None or table16 is None:
+                raise ValueError("precision='bf16s' needs theta16 and table16 (see shadow_bf16)")
+            rc = self.lib.estk_eval_mlp_bf16s(self._ctx, C.byref(d), th, self._ptr(theta16, torch.bfloat16, "theta16"),
+                                              tb, self._ptr(table16, torch.bfloat16, "table16"), *common)
+        elif precision == "bf16":
+            rc = self.lib.estk_eval_mlp_bf16(self._ctx, C.byref(d), th, tb, *common)
+        elif precision == "fp32":
+            rc = self.lib.estk_eval_mlp(self._ctx, C.byref(d), th, tb, *common)
+        else:
+            raise ValueError(f"unknown precision {precision!r}")
+        _capi.check(rc, "estk_eval_mlp[" + precision + "]")
         self.launches += 1
 
     def eval_mlp_center(self, dims, theta, obs, target, ret_out, bc_out=None, bc_obs=0, bc_dim=0,
-                        precision="fp32"):
+                        precision="fp32", theta16=None):
         d = mlp_desc(dims)
-        fn = self.lib.estk_eval_mlp_center_bf16 if precision == "bf16" else self.lib.estk_eval_mlp_center
-        _capi.check(fn(
-            self._ctx, C.byref(d), self._ptr(theta, torch.float32, "theta"),
-            self._ptr(obs, torch.float32, "obs"), self._ptr(target, torch.float32, "target"),
-            int(obs.shape[0]), self._ptr(ret_out, torch.float32, "ret_out"),
-            self._ptr(bc_out, torch.float32, "bc_out"), int(bc_obs), int(bc_dim), self._stream()),
-            "estk_eval_mlp_center")
+        tail = (self._ptr(obs, torch.float32, "obs"), self._ptr(target, torch.float32, "target"),
+                int(obs.shape[0]), self._ptr(ret_out, torch.float32, "ret_out"),
+                self._ptr(bc_out, torch.float32, "bc_out"), int(bc_obs), int(bc_dim), self._stream())
+        th = self._ptr(theta, torch.float32, "theta")
+        if precision == "bf16s":
+            rc = self.lib.estk_eval_mlp_center_bf16s(self._ctx, C.byref(d), th,
+                                                     self._ptr(theta16, torch.bfloat16, "theta16"), *tail)
+        elif precision == "bf16":
+            rc = self.lib.estk_eval_mlp_center_bf16(self._ctx, C.byref(d), th, *tail)
+        else:
+            rc = self.lib.estk_eval_mlp_center(self._ctx, C.byref(d), th, *tail)
+        _capi.check(rc, "estk_eval_mlp_center[" + precision + "]")
         self.launches += 1
 
     def track_best(self, state, reward, theta, best_theta):

@@ -50,6 +50,8 @@ struct EvalTCParams {
   estk_mlp_desc desc;
   const float* theta;
   const float* table;
+  const uint16_t* theta16;  // optional bf16 shadows of theta / table (both or neither):
+  const uint16_t* table16;  // producer sources at half the bytes (precision mode "bf16s")
   const int64_t* offsets;  // null => centre evaluation
   const int32_t* order;
   int pairs;
@@ -198,6 +200,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ uint4 ld_noise4u(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 // UMMA shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 //  version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64)).
@@ -235,7 +243,7 @@ struct Layer { int K, N; int64_t wbase, bbase; };
 #define PROF_T() (PROF_ON ? clock64() : 0ll)
 #define PROF_ADD(i, t0) do { if (PROF_ON) atomicAdd(&g_tc_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
 
-template <int CG>
+template <int CG, bool S16>
 __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTCParams p) {
   constexpr int kStages = (CG == 2) ? 4 : 2;
   constexpr int kStageB = (CG == 2) ? kStageBytes : 2 * kStageBytes;   // up to 256 rows at CG=1
@@ -495,9 +503,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     const int pgroup = pwarp / kProdGroupWarps;
     const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // 0..127 inside the group
     constexpr int kPT = 32 * kProdGroupWarps;
-    struct StageDesc { const float* th; const float* ep; int K; int n_items; float ssig; };
+    struct StageDesc { const float* th; const float* ep; const uint16_t* th16; const uint16_t* ep16; int K; int n_items; float ssig; };
+    constexpr bool src16 = S16;
     int cached_task = -1;
     const float* cached_trow = p.theta;
+    const uint16_t* cached_trow16 = p.theta16;
     float cached_ssig = 0.f;
     auto setup = [&](int task, int l, int n0, int kb, StageDesc& d) {
       if (task != cached_task) {            // two dependent global loads: once per task, not per stage
@@ -505,7 +515,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
         const int sgn = (task / p.chunks) % p.n_signs;
         const int slot = task / (p.chunks * p.n_signs);
         const int j = p.order ? p.order[slot] : slot;
-        cached_trow = centre ? p.theta : p.table + p.offsets[j];
+        const int64_t off_j = centre ? 0 : p.offsets[j];
+        cached_trow = centre ? p.theta : p.table + off_j;
+        cached_trow16 = centre ? p.theta16 : p.table16 + off_j;
         cached_ssig = centre ? 0.f : (sgn ? -p.sigma : p.sigma);
       }
       const int K = lay[l].K;
@@ -513,6 +525,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       const int64_t rbase = lay[l].wbase + (int64_t)(n0 + (int)cta_rank * rows) * K + kb * kBlockK;
       d.th = p.theta + rbase;
       d.ep = cached_trow + rbase;
+      d.th16 = p.theta16 + rbase;
+      d.ep16 = cached_trow16 + rbase;
       d.K = K;
       d.n_items = rows * 8;                                    // 16-byte output chunks
       d.ssig = cached_ssig;
@@ -543,40 +557,82 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       if (pprof) atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - ts0));
       const uint32_t sbase = smem_u32(sB + stage * kStageB);
       bool waited = false;
+      if constexpr (src16) {
+        // bf16 shadow sources: one 128-bit load brings 8 elements, so a batch of 8
+        // items per thread (16 loads in flight) covers a whole [128 x 64] stage
+        for (int it0 = 0; it0 < cur.n_items; it0 += 8 * kPT) {
+          uint4 t16[8], e16[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int it = it0 + u * kPT + ptid;
+            if (it < cur.n_items && !(p.dbg & 1)) {
+              const int64_t off = (int64_t)(it >> 3) * cur.K + (it & 7) * 8;
+              t16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.th16 + off));
+              e16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.ep16 + off));
+            }
+          }
+          if (!waited) {
+            const long long tw0 = pprof ? clock64() : 0ll;
+            mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
+            waited = true;
+            if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
+          }
+          const long long tc0 = pprof ? clock64() : 0ll;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int it = it0 + u * kPT + ptid;
+            if (it < cur.n_items) {
+              const float sg = cur.ssig;
+              const uint32_t tw[4] = {t16[u].x, t16[u].y, t16[u].z, t16[u].w};
+              const uint32_t ew[4] = {e16[u].x, e16[u].y, e16[u].z, e16[u].w};
+              uint32_t w[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {      // each 32-bit word holds two bf16 (low = even element)
+                const float lo = fmaf(sg, __uint_as_float(ew[c] << 16), __uint_as_float(tw[c] << 16));
+                const float hi = fmaf(sg, __uint_as_float(ew[c] & 0xFFFF0000u), __uint_as_float(tw[c] & 0xFFFF0000u));
+                w[c] = pack_bf16(lo, hi);
+              }
+              st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w[0], w[1], w[2], w[3]);
+            }
+          }
+          if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
+        }
+      } else {
       for (int it0 = 0; it0 < cur.n_items; it0 += 4 * kPT) {
-        // every 128-bit load of the batch is issued up front (16 in flight per thread) ...
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int it = it0 + u * kPT + ptid;
-          if (it < cur.n_items && !(p.dbg & 1)) {
-            const int64_t off = (int64_t)(it >> 3) * cur.K + (it & 7) * 8;
-            th[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off));
-            th[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off + 4));
-            ep[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.ep + off));
-            ep[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.ep + off + 4));
+          // every 128-bit load of the batch is issued up front (16 in flight per thread) ...
+  #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * kPT + ptid;
+            if (it < cur.n_items && !(p.dbg & 1)) {
+              const int64_t off = (int64_t)(it >> 3) * cur.K + (it & 7) * 8;
+              th[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off));
+              th[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off + 4));
+              ep[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.ep + off));
+              ep[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.ep + off + 4));
+            }
           }
-        }
-        // ... then wait for the ring slot (almost always free already)
-        if (!waited) {
-          const long long tw0 = pprof ? clock64() : 0ll;
-          mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
-          waited = true;
-          if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
-        }
-        const long long tc0 = pprof ? clock64() : 0ll;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int it = it0 + u * kPT + ptid;
-          if (it < cur.n_items) {
-            const float sg = cur.ssig;
-            const uint32_t w0 = pack_bf16(fmaf(sg, ep[u][0].x, th[u][0].x), fmaf(sg, ep[u][0].y, th[u][0].y));
-            const uint32_t w1 = pack_bf16(fmaf(sg, ep[u][0].z, th[u][0].z), fmaf(sg, ep[u][0].w, th[u][0].w));
-            const uint32_t w2 = pack_bf16(fmaf(sg, ep[u][1].x, th[u][1].x), fmaf(sg, ep[u][1].y, th[u][1].y));
-            const uint32_t w3 = pack_bf16(fmaf(sg, ep[u][1].z, th[u][1].z), fmaf(sg, ep[u][1].w, th[u][1].w));
-            st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
+          // ... then wait for the ring slot (almost always free already)
+          if (!waited) {
+            const long long tw0 = pprof ? clock64() : 0ll;
+            mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
+            waited = true;
+            if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
           }
+          const long long tc0 = pprof ? clock64() : 0ll;
+  #pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * kPT + ptid;
+            if (it < cur.n_items) {
+              const float sg = cur.ssig;
+              const uint32_t w0 = pack_bf16(fmaf(sg, ep[u][0].x, th[u][0].x), fmaf(sg, ep[u][0].y, th[u][0].y));
+              const uint32_t w1 = pack_bf16(fmaf(sg, ep[u][0].z, th[u][0].z), fmaf(sg, ep[u][0].w, th[u][0].w));
+              const uint32_t w2 = pack_bf16(fmaf(sg, ep[u][1].x, th[u][1].x), fmaf(sg, ep[u][1].y, th[u][1].y));
+              const uint32_t w3 = pack_bf16(fmaf(sg, ep[u][1].z, th[u][1].z), fmaf(sg, ep[u][1].w, th[u][1].w));
+              st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
+            }
+          }
+          if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
         }
-        if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
       }
       const long long tf0 = pprof ? clock64() : 0ll;
       fence_proxy_async();
@@ -604,10 +660,10 @@ size_t tc_smem_bytes() {
          (2 * stages + 2) * sizeof(uint64_t) + 128;
 }
 
-template <int CG>
+template <int CG, bool S16>
 int launch_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream) {
   const size_t smem = tc_smem_bytes<CG>();
-  ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_tc_kernel<CG, S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int clusters = ctx->sm_count / CG;
   if (clusters > p.n_tasks) clusters = p.n_tasks;
   cudaLaunchConfig_t cfg = {};
@@ -622,7 +678,7 @@ int launch_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_tc_kernel<CG>, p));
+  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_tc_kernel<CG, S16>, p));
   return ESTK_OK;
 }
 
@@ -652,7 +708,7 @@ int run_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream, const char* who)
   { const char* e = getenv("ESTK_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.partial = ctx->eval_partial;
   p.counters = ctx->counters;
-  return launch_tc<2>(ctx, p, stream);
+  return p.theta16 ? launch_tc<2, true>(ctx, p, stream) : launch_tc<2, false>(ctx, p, stream);
 }
 
 }  // namespace
@@ -688,6 +744,65 @@ extern "C" int estk_eval_mlp_center_bf16(estk_ctx* ctx, const estk_mlp_desc* des
   p.bc_plus = bc_out; p.bc_minus = nullptr; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
   p.n_signs = 1;
   return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_center_bf16");
+}
+
+__global__ void __launch_bounds__(256) shadow_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = src[i];
+    uint2 o;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v.w), "f"(v.z));
+    dst[i] = o;
+  }
+}
+
+extern "C" int estk_shadow_bf16(estk_ctx* ctx, const float* src, uint16_t* dst, int64_t n, void* stream) {
+  ESTK_CHECK_ARG(ctx && src && dst && n > 0 && (n % 4) == 0, "estk_shadow_bf16: null argument or n not a multiple of 4");
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(src) && ((uintptr_t)dst & 7u) == 0, "estk_shadow_bf16: unaligned buffers");
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  shadow_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src),
+                                                             reinterpret_cast<uint2*>(dst), n / 4);
+  ESTK_CUDA(cudaGetLastError());
+  return ESTK_OK;
+}
+
+extern "C" int estk_eval_mlp_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                                   const uint16_t* theta16, const float* table, const uint16_t* table16,
+                                   const int64_t* offsets, const int32_t* order, int32_t pairs, float sigma,
+                                   const float* obs, const float* target, int32_t B, float* returns_plus,
+                                   float* returns_minus, float* bc_plus, float* bc_minus, int32_t bc_obs,
+                                   int32_t bc_dim, void* stream) {
+  ESTK_CHECK_ARG(ctx && desc && theta && theta16 && table && table16 && offsets && obs && target &&
+                 returns_plus && returns_minus, "estk_eval_mlp_bf16s: null argument");
+  ESTK_CHECK_ARG((bc_plus == nullptr) == (bc_minus == nullptr), "estk_eval_mlp_bf16s: bc_plus/bc_minus must both be set or both null");
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(table) && ESTK_ALIGNED16(obs) && ESTK_ALIGNED16(target) &&
+                 ESTK_ALIGNED16(theta16) && ESTK_ALIGNED16(table16),
+                 "estk_eval_mlp_bf16s: buffers must be 16-byte aligned");
+  EvalTCParams p = {};
+  p.desc = *desc; p.theta = theta; p.table = table; p.theta16 = theta16; p.table16 = table16;
+  p.offsets = offsets; p.order = order;
+  p.pairs = pairs; p.sigma = sigma; p.obs = obs; p.target = target; p.B = B;
+  p.ret_plus = returns_plus; p.ret_minus = returns_minus;
+  p.bc_plus = bc_plus; p.bc_minus = bc_minus; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
+  p.n_signs = 2;
+  return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_bf16s");
+}
+
+extern "C" int estk_eval_mlp_center_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                                          const uint16_t* theta16, const float* obs, const float* target,
+                                          int32_t B, float* return_out, float* bc_out, int32_t bc_obs,
+                                          int32_t bc_dim, void* stream) {
+  ESTK_CHECK_ARG(ctx && desc && theta && theta16 && obs && target && return_out, "estk_eval_mlp_center_bf16s: null argument");
+  EvalTCParams p = {};
+  p.desc = *desc; p.theta = theta; p.table = theta; p.theta16 = theta16; p.table16 = theta16;
+  p.offsets = nullptr; p.order = nullptr;
+  p.pairs = 1; p.sigma = 0.f; p.obs = obs; p.target = target; p.B = B;
+  p.ret_plus = return_out; p.ret_minus = nullptr;
+  p.bc_plus = bc_out; p.bc_minus = nullptr; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
+  p.n_signs = 1;
+  return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_center_bf16s");
 }
 
 extern "C" int estk_eval_mlp_bf16_supported(const estk_mlp_desc* desc, int32_t B) {

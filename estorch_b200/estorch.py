@@ -102,6 +102,7 @@ class _PolicySlot:
         self.best_theta = be.zeros(self.n)
         self.theta_prev = be.zeros(self.n)     # centre of the last sampled population
         self.state = new_state(be.device)
+        self.theta16 = None                    # bf16 shadow of theta (eval_precision="bf16s")
         self.flattened = flatten
         with torch.no_grad():
             self.theta.copy_(torch.nn.utils.parameters_to_vector(params).detach().to(be.device))
@@ -167,7 +168,9 @@ class ES:
             reference behaviour).
         eval_precision: arithmetic of the fused evaluate kernel: ``"fp32"`` (exact
             CUDA-core path), ``"bf16"`` (tcgen05 tensor cores, bf16 operands, fp32
-            accumulation) or ``"auto"`` (bf16 when the policy shape supports it).
+            accumulation), ``"bf16s"`` (as bf16, with the weight producers reading bf16
+            shadows of theta and the noise table -- half the bytes) or ``"auto"`` (bf16
+            when the policy shape supports it).
     Attributes as documented at estorch.py:108-117.
     """
 
@@ -207,16 +210,16 @@ class ES:
         self._spec = mlp_spec_from_module(self.target)
         self._fused = self._decide_fused(optimizer)
         self._host_cache = {}
-        if eval_precision not in ("auto", "fp32", "bf16"):
-            raise ValueError("eval_precision must be 'auto', 'fp32' or 'bf16'")
+        if eval_precision not in ("auto", "fp32", "bf16", "bf16s"):
+            raise ValueError("eval_precision must be 'auto', 'fp32', 'bf16' or 'bf16s'")
         self._precision = "fp32"
         if self._fused and eval_precision != "fp32":
             supported = getattr(self._be, "eval_supports_bf16", lambda d, b: False)(
                 self._spec.dims, self.agent.obs.shape[0])
-            if eval_precision == "bf16" and not supported:
-                raise ValueError("eval_precision='bf16' needs layer widths that are multiples of 64 (in) / "
+            if eval_precision in ("bf16", "bf16s") and not supported:
+                raise ValueError("eval_precision='bf16[s]' needs layer widths that are multiples of 64 (in) / "
                                  "32 (out), at most 512, and a batch that is a multiple of 256")
-            self._precision = "bf16" if supported else "fp32"
+            self._precision = (eval_precision if eval_precision != "auto" else "bf16") if supported else "fp32"
 
         # ---- noise table (replicated on every GPU, identical by construction)
         n_pad = (self.n_parameters + 31) // 32 * 32
@@ -224,6 +227,10 @@ class ES:
         size = max(size, n_pad + 32) // 32 * 32
         self._table = self._be.alloc(size)
         self._be.fill_noise_table(self._table, self._noise_seed)
+        self._table16 = None
+        if self._precision == "bf16s":
+            self._table16 = self._be.alloc(size, dtype=torch.bfloat16)
+            self._be.shadow_bf16(self._table, self._table16)
 
         # ---- population bookkeeping
         P, W = self.population_size, self.n_workers
@@ -467,6 +474,21 @@ class ES:
         g = optimizer.param_groups[0]
         return adam_desc(lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], clamp=1.0)
 
+    def _eval_kw(self, slot, centre=False):
+        """precision + (for "bf16s") refreshed bf16 shadows for the evaluate kernels."""
+        kw = {"precision": self._precision}
+        if self._precision == "bf16s":
+            if slot.theta16 is None:
+                slot.theta16 = self._be.alloc(slot.n, dtype=torch.bfloat16)
+            self._be.shadow_bf16(slot.theta, slot.theta16)
+            kw["theta16"] = slot.theta16
+            if not centre:
+                if self._table16 is None:      # table was replaced after construction (tests)
+                    self._table16 = self._be.alloc(self._table.numel(), dtype=torch.bfloat16)
+                    self._be.shadow_bf16(self._table, self._table16)
+                kw["table16"] = self._table16
+        return kw
+
     def _upload_batch(self):
         nb = self.agent.next_batch(self.step)
         if nb is not None:
@@ -484,7 +506,7 @@ class ES:
         R = self._returns
         be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
                     self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
-                    precision=self._precision)
+                    **self._eval_kw(slot))
         self._all_gather_halves(R)
         ad = self._adam_desc(slot.optimizer)
         if self.n_workers == 1:
@@ -495,7 +517,7 @@ class ES:
                          self.n_parameters, self._grad, self._ranks, None)
             self._all_reduce(self._grad)
             be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
-        be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, precision=self._precision)
+        be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, **self._eval_kw(slot, True))
         be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
         self._best_slot = slot
 
@@ -666,7 +688,7 @@ class NS_ES(ES):
             slot = self._slots[-1]
             self._be.eval_mlp_center(self._spec.dims, slot.theta, self._obs, self._tgt, self._episode,
                                      self._bc_center[0], self.agent.bc_obs, self.agent.bc_dim,
-                                     precision=self._precision)
+                                     **self._eval_kw(slot, True))
             return float(self._episode.item()), self._bc_center[0].cpu().numpy().copy()
         with torch.no_grad():
             return self.agent.rollout(policy)
@@ -731,7 +753,7 @@ class NS_ES(ES):
         nov = []
         for s in self._slots:
             be.eval_mlp_center(dims, s.theta, self._obs, self._tgt, self._episode, self._bc_center[0],
-                               self.agent.bc_obs, self.agent.bc_dim, precision=self._precision)
+                               self.agent.bc_obs, self.agent.bc_dim, **self._eval_kw(s, True))
             be.knn_novelty(self._bc_center, arch, self.k, self._nov_center)
             nov.append(self._nov_center.clone())
         total = torch.cat(nov).double().cpu().numpy()
@@ -754,7 +776,7 @@ class NS_ES(ES):
         be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
                     self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
                     BC[pb: pb + pl], BC[pairs + pb: pairs + pb + pl], ag.bc_obs, ag.bc_dim,
-                    precision=self._precision)
+                    **self._eval_kw(slot))
         be.knn_novelty(BC[pb: pb + pl], self._arch_dev, self.k, N[pb: pb + pl])
         be.knn_novelty(BC[pairs + pb: pairs + pb + pl], self._arch_dev, self.k, N[pairs + pb: pairs + pb + pl])
         self._all_gather_halves(R)
@@ -772,7 +794,7 @@ class NS_ES(ES):
         # _after_optimize (estorch.py:427-432 / :650-662): rollout of the updated
         # policy, archive append, best tracking, NSRA schedule (host scalars)
         be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, self._bc_center[0],
-                           ag.bc_obs, ag.bc_dim, precision=self._precision)
+                           ag.bc_obs, ag.bc_dim, **self._eval_kw(slot, True))
         episode = float(self._episode.item())
         self._archive.append(self._bc_center[0].cpu().numpy().copy())
         self.episode_reward = episode

@@ -149,6 +149,25 @@ ESTK_API int estk_eval_mlp_center_bf16(estk_ctx* ctx, const estk_mlp_desc* desc,
                               void* stream);
 ESTK_API int estk_eval_mlp_bf16_supported(const estk_mlp_desc* desc, int32_t B);
 
+/* "bf16s": as estk_eval_mlp_bf16, but the weight producers read bf16 SHADOWS of
+ * theta and of the noise table (theta16[i] = bf16(theta[i]), table16[i] =
+ * bf16(table[i]), built with estk_shadow_bf16) -- half the bytes per weight
+ * element, W = bf16(theta16 + s*sigma*table16[off+i]).  Biases still come from the
+ * fp32 theta / table.  The gradient estimate (estk_rank_grad*) always uses the
+ * fp32 table.  Tolerance vs the fp32 path is stated in tests/test_kernels_gpu.py. */
+ESTK_API int estk_shadow_bf16(estk_ctx* ctx, const float* src, uint16_t* dst, int64_t n, void* stream);
+ESTK_API int estk_eval_mlp_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                        const uint16_t* theta16, const float* table, const uint16_t* table16,
+                        const int64_t* offsets, const int32_t* order, int32_t pairs, float sigma,
+                        const float* obs, const float* target, int32_t B,
+                        float* returns_plus, float* returns_minus,
+                        float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim,
+                        void* stream);
+ESTK_API int estk_eval_mlp_center_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                               const uint16_t* theta16, const float* obs, const float* target, int32_t B,
+                               float* return_out, float* bc_out, int32_t bc_obs, int32_t bc_dim,
+                               void* stream);
+
 /* Unperturbed policy (estorch.py:181-182 `_after_optimize` rollout):
  * return_out[0] = return of theta; bc_out (nullable) [bc_dim]. */
 ESTK_API int estk_eval_mlp_center(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,

@@ -32,7 +32,7 @@ __all__ = [
     "compute_ranks", "center_values", "rank_transformation",
     "mix64", "noise_slots", "noise_offsets", "philox4x32_10", "philox_normal_table",
     "mlp_param_count", "mlp_unflatten", "mlp_forward", "mlp_forward_bf16", "round_bf16", "synthetic_return", "synthetic_bc",
-    "sample_population", "evaluate_population",
+    "sample_population", "sample_population_bf16s", "evaluate_population",
     "blend_weights", "calculate_grad", "calculate_grad_pairs", "negate_clamp",
     "adam_step", "novelty", "nsra_weight_update", "vbn_stats", "vbn_normalize",
     "conv2d_nchw", "atari_param_layout", "atari_forward",
@@ -237,6 +237,18 @@ def sample_population(theta: np.ndarray, table: np.ndarray, offsets: np.ndarray,
     eps = (np.float32(sigma) * t).astype(np.float32)
     pop = np.concatenate([theta[None, :] + eps, theta[None, :] - eps]).astype(np.float32)
     return pop, np.concatenate([eps, -eps]).astype(np.float32)
+
+
+def sample_population_bf16s(theta: np.ndarray, table: np.ndarray, offsets: np.ndarray, sigma: float):
+    """Rows as the "bf16s" evaluate path forms them (estk_eval_mlp_bf16s):
+    W = bf16(theta) +- sigma * bf16(T[off:off+n]) in fp32 (one fma), later rounded
+    to bf16 by mlp_forward_bf16.  NOTE: biases come from the fp32 theta / table in
+    the kernel; use ``bias_from`` = the exact rows for those entries."""
+    n = theta.shape[0]
+    t16 = np.stack([round_bf16(table[o:o + n]) for o in offsets])
+    th16 = round_bf16(theta)[None, :]
+    eps = (np.float32(sigma) * t16.astype(np.float64)).astype(np.float64)
+    return np.concatenate([th16 + eps, th16 - eps]).astype(np.float32)
 
 
 def evaluate_population(pop: np.ndarray, dims, obs, target,

@@ -51,7 +51,7 @@ class OracleBackend:
             eps_out.copy_(torch.from_numpy(eps[sl]))
 
     def eval_mlp(self, dims, theta, table, offsets, order, pairs, sigma, obs, target, ret_plus, ret_minus,
-                 bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32"):
+                 bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32", **_):
         pop, _ = orc.sample_population(_np(theta), _np(table), _np(offsets), sigma)
         rets, bcs = orc.evaluate_population(pop, list(dims), _np(obs), _np(target), bc_obs, bc_dim)
         ret_plus.copy_(torch.from_numpy(rets[:pairs]))
@@ -60,7 +60,7 @@ class OracleBackend:
             bc_plus.copy_(torch.from_numpy(bcs[:pairs]))
             bc_minus.copy_(torch.from_numpy(bcs[pairs:]))
 
-    def eval_mlp_center(self, dims, theta, obs, target, ret_out, bc_out=None, bc_obs=0, bc_dim=0, precision="fp32"):
+    def eval_mlp_center(self, dims, theta, obs, target, ret_out, bc_out=None, bc_obs=0, bc_dim=0, precision="fp32", **_):
         out = orc.mlp_forward(_np(theta), list(dims), _np(obs))
         ret_out[0] = float(orc.synthetic_return(out, _np(target)))
         if bc_out is not None:

@@ -394,3 +394,51 @@ def test_eval_mlp_bf16_tensor_core_path(be, dims, B, pairs, bc):
     with pytest.raises(RuntimeError, match="not supported"):
         be.eval_mlp([4, 64, 2], dev(be, theta[:450]), dev(be, table), dev(be, offs), None, pairs, 0.02,
                     dev(be, obs[:, :4].copy()), dev(be, tgt[:, :2].copy()), ret[:pairs], ret[pairs:], precision="bf16")
+
+
+@pytest.mark.parametrize("dims,B,pairs", [([128, 512, 512, 288], 256, 4), ([64, 256, 64], 512, 3),
+                                          ([128, 512, 512, 512, 512, 288], 256, 2)])
+def test_eval_mlp_bf16s_shadow_sources(be, dims, B, pairs):
+    """"bf16s": producers read bf16 shadows of theta / table.  Within 5e-4 of the oracle
+    that emulates exactly those roundings, within 3e-2 of the exact fp32 forward."""
+    rng = np.random.RandomState(17)
+    n = orc.mlp_param_count(dims)
+    table_len = (n + 31) // 32 * 32 + (1 << 14)
+    table = rng.standard_normal(table_len).astype(np.float32)
+    theta = np.concatenate([np.concatenate([(rng.uniform(-1, 1, dims[i] * dims[i + 1]) / np.sqrt(dims[i])),
+                                            rng.uniform(-1, 1, dims[i + 1]) / np.sqrt(dims[i])])
+                            for i in range(len(dims) - 1)]).astype(np.float32)
+    obs = rng.standard_normal((B, dims[0])).astype(np.float32)
+    tgt = rng.standard_normal((B, dims[-1])).astype(np.float32)
+    offs = orc.noise_offsets(11, 0, 0, pairs, table_len, n)
+    th, tb = dev(be, theta), dev(be, table)
+    th16 = be.alloc(n, dtype=torch.bfloat16)
+    tb16 = be.alloc(table_len, dtype=torch.bfloat16)
+    be.shadow_bf16(th, th16)
+    be.shadow_bf16(tb, tb16)
+    np.testing.assert_array_equal(th16.float().cpu().numpy(), orc.round_bf16(theta))   # cvt.rn == RNE
+    ret = be.zeros(2 * pairs)
+    be.eval_mlp(dims, th, tb, dev(be, offs), None, pairs, 0.02, dev(be, obs), dev(be, tgt),
+                ret[:pairs], ret[pairs:], precision="bf16s", theta16=th16, table16=tb16)
+    got = ret.cpu().numpy()
+    exact_rows, _ = orc.sample_population(theta, table, offs, 0.02)
+    rows = orc.sample_population_bf16s(theta, table, offs, 0.02)
+    idx = 0
+    for i in range(len(dims) - 1):                      # biases are formed from the fp32 sources
+        idx += dims[i] * dims[i + 1]
+        rows[:, idx: idx + dims[i + 1]] = exact_rows[:, idx: idx + dims[i + 1]]
+        idx += dims[i + 1]
+    emu = np.array([orc.synthetic_return(orc.mlp_forward_bf16(r, dims, obs), tgt) for r in rows], dtype=np.float32)
+    exact, _ = orc.evaluate_population(exact_rows, dims, obs, tgt)
+    assert rel_err(got, emu) < 5e-4
+    assert rel_err(got, exact) < 3e-2
+    one = be.zeros(1)
+    be.eval_mlp_center(dims, th, dev(be, obs), dev(be, tgt), one, precision="bf16s", theta16=th16)
+    crow = orc.round_bf16(theta).copy()
+    idx = 0
+    for i in range(len(dims) - 1):
+        idx += dims[i] * dims[i + 1]
+        crow[idx: idx + dims[i + 1]] = theta[idx: idx + dims[i + 1]]
+        idx += dims[i + 1]
+    want = float(orc.synthetic_return(orc.mlp_forward_bf16(crow, dims, obs), tgt))
+    assert abs(float(one) - want) < 5e-4 * abs(want)

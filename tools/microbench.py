@@ -86,6 +86,14 @@ def main():
             print(json.dumps({"kernel": "eval_mlp_bf16", "config": name, "pairs": pairs, "B": B, "ms_median": med,
                               "ms_best": best, "TFLOPs": flops / med / 1e9, "frac_tensor": flops / med / 1e9 / 1431.4}),
                   flush=True)
+            th16 = be.alloc(n, dtype=torch.bfloat16); tb16 = be.alloc(table_len, dtype=torch.bfloat16)
+            be.shadow_bf16(theta, th16); be.shadow_bf16(table, tb16)
+            med, best = timeit(lambda: be.eval_mlp(dims, theta, table, offs, order, pairs, 0.02, obs, tgt,
+                                                    rets2[:pairs], rets2[pairs:], precision="bf16s",
+                                                    theta16=th16, table16=tb16), iters=5, warmup=2)
+            print(json.dumps({"kernel": "eval_mlp_bf16s", "config": name, "pairs": pairs, "B": B, "ms_median": med,
+                              "ms_best": best, "TFLOPs": flops / med / 1e9, "frac_tensor": flops / med / 1e9 / 1431.4}),
+                  flush=True)
             one = be.zeros(1)
             med, best = timeit(lambda: be.eval_mlp_center(dims, theta, obs, tgt, one, precision="bf16"), iters=5, warmup=2)
             print(json.dumps({"kernel": "eval_mlp_center_bf16", "config": name, "ms_median": med}), flush=True)
