@@ -308,16 +308,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
         for (int l = 0; l < L; ++l) {
           const long long th0 = PROF_T();
-          mbar_wait(smem_u32(bar_h), h_phase);
+          mbar_wait(smem_u32(bar_h), h_phase);     // k-blocks 0..3 of this layer's input are in place
           PROF_ADD(1, th0);
           h_phase ^= 1;
           tc_fence_after();
           const int K = lay[l].K, N = lay[l].N;
+          bool second_half_ready = (K <= 256) || (l == 0);   // hidden inputs wider than 256 arrive in two halves
           for (int n0 = 0; n0 < N; n0 += 256) {
             const int Ng = min(256, N - n0);
             const uint32_t idesc = make_idesc(128 * CG, Ng);
             const uint32_t tmem_d = tmem_base + (uint32_t)n0;
             for (int kb = 0; kb < K / kBlockK; ++kb) {
+              if (kb == 4 && !second_half_ready) {   // k-blocks 4..7 (and TMEM columns >= 256 drained)
+                const long long th1 = PROF_T();
+                mbar_wait(smem_u32(bar_h), h_phase);
+                PROF_ADD(1, th1);
+                h_phase ^= 1;
+                tc_fence_after();
+                second_half_ready = true;
+              }
               const long long tf0 = PROF_T();
               mbar_wait(smem_u32(bar_full + stage), ring_phase);
               PROF_ADD(2, tf0);
@@ -389,11 +398,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
         float* bias = sBias + (l & 1) * kMaxW;
         for (int o = etid; o < N; o += 32 * kNumEpiWarps)
           bias[o] = fmaf(ssig, ld_noise1(trow + lay[l].bbase + o), __ldg(p.theta + lay[l].bbase + o));
-        // H (and, for l > 0, the previous layer's TMEM reads) are done: release the MMA warp
-        fence_proxy_async();
-        tc_fence_before();
-        named_bar_sync(1, 32 * kNumEpiWarps);   // also publishes bias[] among the epilogue warps
-        if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h), 0);
+        named_bar_sync(1, 32 * kNumEpiWarps);   // publishes bias[] among the epilogue warps
+        if (l == 0) {
+          // the staged observations are this task's layer-0 input (the previous task's
+          // TMEM reads are long done): release the MMA warp
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h), 0);   // layer 0: one hand-over for the whole input
+        }
         if (eprof) atomicAdd(&g_tc_prof[12], (unsigned long long)(clock64() - tb0));
         // ---- wait for the layer's accumulators
         const long long ta0 = eprof ? clock64() : 0ll;
@@ -448,7 +461,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           }
         };
         const uint32_t trow_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        // this layer's output is the next layer's input: hand it over in halves so the
+        // next layer's MMAs on k-blocks 0..3 (which only overwrite TMEM columns < 256,
+        // already drained) overlap the second half of this epilogue
+        auto hand_over = [&]() {
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h), 0);
+        };
         for (int c0 = 0; c0 < N && !(p.dbg & 2); c0 += 32) {
+          if (!last && c0 == 256) hand_over();
           uint32_t va[32];
           const long long tl0 = eprof ? clock64() : 0ll;
           tmem_ld32(trow_addr + (uint32_t)c0, va);
@@ -464,6 +487,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           if (eprof) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - tl0));
           consume(va, c0);
         }
+        if (!last) hand_over();                  // second half (or the only one when N <= 256)
         if (eprof) atomicAdd(&g_tc_prof[14], (unsigned long long)(clock64() - tx0));
       }
       // ---- squared-error partial of this CTA; the last arriver combines them in fixed order
@@ -582,16 +606,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           for (int u = 0; u < 8; ++u) {
             const int it = it0 + u * kPT + ptid;
             if (it < cur.n_items) {
-              const float sg = cur.ssig;
+              // W = theta16 + (s*sigma)_bf16 * eps16, one packed fma per two elements
+              // (exact product-sum, one rounding to bf16; sigma itself is rounded to bf16)
+              const uint32_t sg2 = pack_bf16(cur.ssig, cur.ssig);
               const uint32_t tw[4] = {t16[u].x, t16[u].y, t16[u].z, t16[u].w};
               const uint32_t ew[4] = {e16[u].x, e16[u].y, e16[u].z, e16[u].w};
               uint32_t w[4];
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {      // each 32-bit word holds two bf16 (low = even element)
-                const float lo = fmaf(sg, __uint_as_float(ew[c] << 16), __uint_as_float(tw[c] << 16));
-                const float hi = fmaf(sg, __uint_as_float(ew[c] & 0xFFFF0000u), __uint_as_float(tw[c] & 0xFFFF0000u));
-                w[c] = pack_bf16(lo, hi);
-              }
+              for (int c = 0; c < 4; ++c)
+                asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(w[c]) : "r"(sg2), "r"(ew[c]), "r"(tw[c]));
               st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w[0], w[1], w[2], w[3]);
             }
           }

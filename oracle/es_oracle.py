@@ -241,14 +241,17 @@ def sample_population(theta: np.ndarray, table: np.ndarray, offsets: np.ndarray,
 
 def sample_population_bf16s(theta: np.ndarray, table: np.ndarray, offsets: np.ndarray, sigma: float):
     """Rows as the "bf16s" evaluate path forms them (estk_eval_mlp_bf16s):
-    W = bf16(theta) +- sigma * bf16(T[off:off+n]) in fp32 (one fma), later rounded
-    to bf16 by mlp_forward_bf16.  NOTE: biases come from the fp32 theta / table in
-    the kernel; use ``bias_from`` = the exact rows for those entries."""
+    ``W = bf16(theta16 +- sigma16 * eps16)`` with theta16 = bf16(theta), eps16 =
+    bf16(T[off:off+n]), sigma16 = bf16(sigma) and ONE rounding of the exact
+    product-sum (PTX ``fma.rn.bf16x2``).  Biases are formed from the fp32 sources in
+    the kernel -- the caller patches those entries with the exact rows."""
     n = theta.shape[0]
-    t16 = np.stack([round_bf16(table[o:o + n]) for o in offsets])
-    th16 = round_bf16(theta)[None, :]
-    eps = (np.float32(sigma) * t16.astype(np.float64)).astype(np.float64)
-    return np.concatenate([th16 + eps, th16 - eps]).astype(np.float32)
+    t16 = np.stack([round_bf16(table[o:o + n]) for o in offsets]).astype(np.float64)
+    th16 = round_bf16(theta)[None, :].astype(np.float64)
+    s16 = float(round_bf16(np.array([sigma], dtype=np.float32))[0])
+    plus = round_bf16((th16 + s16 * t16).astype(np.float32))     # double -> fp32 -> bf16 (double rounding is rare)
+    minus = round_bf16((th16 - s16 * t16).astype(np.float32))
+    return np.concatenate([plus, minus]).astype(np.float32)
 
 
 def evaluate_population(pop: np.ndarray, dims, obs, target,
