@@ -300,8 +300,9 @@ def run_ours(args, wl, rank, world, local_rank):
             "unit": "generations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "bf16 operands / f32 accumulate (evaluate GEMMs); f32 noise, ranks, reduction, Adam"
-                     if es._precision == "bf16" else "f32",
+            "dtype": {"bf16": "bf16 operands / f32 accumulate (evaluate GEMMs); f32 noise, ranks, reduction, Adam",
+                      "bf16s": "bf16 operands formed from bf16 shadows of theta/noise, f32 accumulate (evaluate "
+                               "GEMMs); f32 noise table, ranks, reduction, Adam"}.get(es._precision, "f32"),
             "data": "synthetic", "config": workload_config(args, wl, world),
             "e2e": {"value": args.steps / e2e_s, "unit": "generations/s",
                     "h2d_bytes_per_step": int(obs.numel() * 4 + tgt.numel() * 4),

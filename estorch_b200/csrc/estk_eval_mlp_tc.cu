@@ -41,7 +41,8 @@ namespace {
 constexpr int kMaxW = 512;            // max layer width (K and N) of this path
 constexpr int kBlockK = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int kKBlockBytes = 128 * kBlockK * 2;   // one [128 x 64] bf16 tile = 16 KB
-constexpr int kStageBytes = kKBlockBytes;         // B ring stage (<= 128 rows per CTA at CG=2)
+constexpr int kSubPerStage = 1;                   // k-blocks per ring stage (2 was measured: no gain, less ring depth)
+constexpr int kStageBytes = kSubPerStage * kKBlockBytes;   // B ring stage: [<=128 rows x 64] per k-block at CG=2
 constexpr int kNumEpiWarps = 4, kNumProdWarps = 8;
 constexpr int kProdGroups = 2, kProdGroupWarps = kNumProdWarps / kProdGroups;   // groups work on different ring stages concurrently
 constexpr int kThreadsTC = 32 * (2 + kNumEpiWarps + kNumProdWarps);   // 320
@@ -226,6 +227,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// relu(x) rounded to bf16, two at a time (ReLU fused into the conversion)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -245,7 +252,7 @@ struct Layer { int K, N; int64_t wbase, bbase; };
 
 template <int CG, bool S16>
 __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTCParams p) {
-  constexpr int kStages = (CG == 2) ? 4 : 2;
+  constexpr int kStages = 4 / kSubPerStage;
   constexpr int kStageB = (CG == 2) ? kStageBytes : 2 * kStageBytes;   // up to 256 rows at CG=1
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -318,8 +325,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             const int Ng = min(256, N - n0);
             const uint32_t idesc = make_idesc(128 * CG, Ng);
             const uint32_t tmem_d = tmem_base + (uint32_t)n0;
-            for (int kb = 0; kb < K / kBlockK; ++kb) {
-              if (kb == 4 && !second_half_ready) {   // k-blocks 4..7 (and TMEM columns >= 256 drained)
+            for (int kb = 0; kb < K / kBlockK; kb += kSubPerStage) {
+              if (kb >= 4 && !second_half_ready) {   // k-blocks 4..7 (and TMEM columns >= 256 drained)
                 const long long th1 = PROF_T();
                 mbar_wait(smem_u32(bar_h), h_phase);
                 PROF_ADD(1, th1);
@@ -327,22 +334,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
                 tc_fence_after();
                 second_half_ready = true;
               }
+              const int nsub = min(kSubPerStage, K / kBlockK - kb);
               const long long tf0 = PROF_T();
               mbar_wait(smem_u32(bar_full + stage), ring_phase);
               PROF_ADD(2, tf0);
               const long long ti0 = PROF_T();
               tc_fence_after();
               if (elect_one()) {
-                const uint32_t a_addr = smem_u32(sH + kb * kKBlockBytes);
-                const uint32_t b_addr = smem_u32(sB + stage * kStageB);
+                for (int sub = 0; sub < nsub; ++sub) {
+                  const uint32_t a_addr = smem_u32(sH + (kb + sub) * kKBlockBytes);
+                  const uint32_t b_addr = smem_u32(sB + stage * kStageB + sub * kKBlockBytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16 && !(p.dbg & 4); ++k) {
-                  const uint64_t da = make_sw128_desc(a_addr + k * 32);
-                  const uint64_t db = make_sw128_desc(b_addr + k * 32);
-                  umma_bf16<CG>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < kBlockK / 16 && !(p.dbg & 4); ++k) {
+                    const uint64_t da = make_sw128_desc(a_addr + k * 32);
+                    const uint64_t db = make_sw128_desc(b_addr + k * 32);
+                    umma_bf16<CG>(tmem_d, da, db, idesc, (kb | sub | k) != 0 ? 1u : 0u);
+                  }
                 }
                 umma_commit<CG>(smem_u32(bar_empty + stage));          // frees the ring slot (both CTAs)
-                if (n0 + 256 >= N && kb == K / kBlockK - 1) umma_commit<CG>(smem_u32(bar_acc));
+                if (n0 + 256 >= N && kb + nsub == K / kBlockK) umma_commit<CG>(smem_u32(bar_acc));
               }
               __syncwarp();
               PROF_ADD(3, ti0);
@@ -431,8 +441,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             uint32_t pk[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e)
-              pk[e] = pack_bf16(fmaxf(__uint_as_float(v[2 * e]) + bv[2 * e], 0.f),
-                                fmaxf(__uint_as_float(v[2 * e + 1]) + bv[2 * e + 1], 0.f));
+              pk[e] = pack_bf16_relu(__uint_as_float(v[2 * e]) + bv[2 * e],
+                                     __uint_as_float(v[2 * e + 1]) + bv[2 * e + 1]);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {      // 4 chunks of 8 output features = 16 bytes of bf16
               const int col = c0 + g * 8;
@@ -476,14 +486,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           const long long tl0 = eprof ? clock64() : 0ll;
           tmem_ld32(trow_addr + (uint32_t)c0, va);
           tmem_ld_wait();
-          if (p.dbg & 16) {            // triage: TMEM read only
-            uint32_t x = 0;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) x ^= va[e];
-            if (x == 0x12345u) loss += 1.f;
-            if (eprof) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - tl0));
-            continue;
-          }
           if (eprof) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - tl0));
           consume(va, c0);
         }
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     const int pgroup = pwarp / kProdGroupWarps;
     const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // 0..127 inside the group
     constexpr int kPT = 32 * kProdGroupWarps;
-    struct StageDesc { const float* th; const float* ep; const uint16_t* th16; const uint16_t* ep16; int K; int n_items; float ssig; };
+    struct StageDesc { const float* th; const float* ep; const uint16_t* th16; const uint16_t* ep16; int K; int n_items; int sub_items; float ssig; };
     constexpr bool src16 = S16;
     int cached_task = -1;
     const float* cached_trow = p.theta;
@@ -552,11 +554,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       d.th16 = p.theta16 + rbase;
       d.ep16 = cached_trow16 + rbase;
       d.K = K;
-      d.n_items = rows * 8;                                    // 16-byte output chunks
+      d.sub_items = rows * 8;                                  // 16-byte output chunks per k-block
+      d.n_items = d.sub_items * min(kSubPerStage, K / kBlockK - kb);
       d.ssig = cached_ssig;
     };
     auto advance = [&](int& task, int& l, int& n0, int& kb) -> bool {
-      if (++kb == lay[l].K / kBlockK) {
+      kb += kSubPerStage;
+      if (kb >= lay[l].K / kBlockK) {
         kb = 0;
         n0 += 256;
         if (n0 >= lay[l].N) {
@@ -590,7 +594,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           for (int u = 0; u < 8; ++u) {
             const int it = it0 + u * kPT + ptid;
             if (it < cur.n_items && !(p.dbg & 1)) {
-              const int64_t off = (int64_t)(it >> 3) * cur.K + (it & 7) * 8;
+              const int sub = it >= cur.sub_items, iq = it - sub * cur.sub_items;
+              const int64_t off = (int64_t)(iq >> 3) * cur.K + sub * kBlockK + (iq & 7) * 8;
               t16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.th16 + off));
               e16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.ep16 + off));
             }
@@ -615,7 +620,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(w[c]) : "r"(sg2), "r"(ew[c]), "r"(tw[c]));
-              st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w[0], w[1], w[2], w[3]);
+              const int sub = it >= cur.sub_items, iq = it - sub * cur.sub_items;
+              st_shared_v4(sbase + sub * kKBlockBytes + sw128_offset(iq >> 3, iq & 7), w[0], w[1], w[2], w[3]);
             }
           }
           if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
@@ -627,7 +633,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           for (int u = 0; u < 4; ++u) {
             const int it = it0 + u * kPT + ptid;
             if (it < cur.n_items && !(p.dbg & 1)) {
-              const int64_t off = (int64_t)(it >> 3) * cur.K + (it & 7) * 8;
+              const int sub = it >= cur.sub_items, iq = it - sub * cur.sub_items;
+              const int64_t off = (int64_t)(iq >> 3) * cur.K + sub * kBlockK + (iq & 7) * 8;
               th[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off));
               th[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off + 4));
               ep[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.ep + off));
@@ -651,7 +658,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
               const uint32_t w1 = pack_bf16(fmaf(sg, ep[u][0].z, th[u][0].z), fmaf(sg, ep[u][0].w, th[u][0].w));
               const uint32_t w2 = pack_bf16(fmaf(sg, ep[u][1].x, th[u][1].x), fmaf(sg, ep[u][1].y, th[u][1].y));
               const uint32_t w3 = pack_bf16(fmaf(sg, ep[u][1].z, th[u][1].z), fmaf(sg, ep[u][1].w, th[u][1].w));
-              st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
+              const int sub = it >= cur.sub_items, iq = it - sub * cur.sub_items;
+              st_shared_v4(sbase + sub * kKBlockBytes + sw128_offset(iq >> 3, iq & 7), w0, w1, w2, w3);
             }
           }
           if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
@@ -677,7 +685,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
 
 template <int CG>
 size_t tc_smem_bytes() {
-  const int stages = (CG == 2) ? 4 : 2;
+  const int stages = 4 / kSubPerStage;
   const int stage_b = (CG == 2) ? kStageBytes : 2 * kStageBytes;
   return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)stages * stage_b + 2 * kMaxW * sizeof(float) +
          (2 * stages + 2) * sizeof(uint64_t) + 128;

@@ -169,8 +169,8 @@ class ES:
         eval_precision: arithmetic of the fused evaluate kernel: ``"fp32"`` (exact
             CUDA-core path), ``"bf16"`` (tcgen05 tensor cores, bf16 operands, fp32
             accumulation), ``"bf16s"`` (as bf16, with the weight producers reading bf16
-            shadows of theta and the noise table -- half the bytes) or ``"auto"`` (bf16
-            when the policy shape supports it).
+            shadows of theta and the noise table -- half the bytes) or ``"auto"``
+            (bf16s when the policy shape supports it, else fp32).
     Attributes as documented at estorch.py:108-117.
     """
 
@@ -219,7 +219,7 @@ class ES:
             if eval_precision in ("bf16", "bf16s") and not supported:
                 raise ValueError("eval_precision='bf16[s]' needs layer widths that are multiples of 64 (in) / "
                                  "32 (out), at most 512, and a batch that is a multiple of 256")
-            self._precision = (eval_precision if eval_precision != "auto" else "bf16") if supported else "fp32"
+            self._precision = (eval_precision if eval_precision != "auto" else "bf16s") if supported else "fp32"
 
         # ---- noise table (replicated on every GPU, identical by construction)
         n_pad = (self.n_parameters + 31) // 32 * 32
@@ -377,7 +377,7 @@ class ES:
         slot.push_theta()
         slot.theta_prev.copy_(slot.theta)
         self._draw_offsets()
-        args = (self._be, slot.theta_prev, self._table, self._offsets_all, self.sigma, self.population_size)
+        args = (self._be, slot.theta_prev, self._table, self._all_offsets(), self.sigma, self.population_size)
         return LazyPopulation(*args), NoiseHandle(*args)
 
     @_builtin
@@ -410,12 +410,19 @@ class ES:
 
     def _draw_offsets(self):
         be = self._be
-        gen = self.step
-        be.make_offsets(self._noise_seed, None, gen, self._pair_begin, self._pairs_local,
+        self._offsets_gen = self.step
+        be.make_offsets(self._noise_seed, None, self.step, self._pair_begin, self._pairs_local,
                         self._table.numel(), self.n_parameters, self._offsets, self._order)
-        if self.n_workers > 1:
-            be.make_offsets(self._noise_seed, None, gen, 0, self._pairs, self._table.numel(),
-                            self.n_parameters, self._offsets_all, None)
+        self._offsets_all_gen = self.step if self.n_workers == 1 else None
+
+    def _all_offsets(self):
+        """Offsets of ALL pairs of the last sampled population (lazy population rows);
+        on multi-GPU runs they are only generated when somebody asks for rows."""
+        if self.n_workers > 1 and getattr(self, "_offsets_all_gen", None) != self._offsets_gen:
+            self._be.make_offsets(self._noise_seed, None, self._offsets_gen, 0, self._pairs,
+                                  self._table.numel(), self.n_parameters, self._offsets_all, None)
+            self._offsets_all_gen = self._offsets_gen
+        return self._offsets_all
 
     def _grad_from(self, epsilon, rewards, novelty, w_rew, w_nov):
         """Gradient estimate for the hooks path: device reduction when ``epsilon``
@@ -453,14 +460,20 @@ class ES:
             dist.all_reduce(t)
 
     def _all_gather_halves(self, t):
-        """Every rank wrote its local pairs' +/- members into ``t``; complete it
-        (replaces the master's Recv loop, estorch.py:228-233)."""
+        """Every rank wrote its local pairs' +/- members into ``t``; complete it with ONE
+        all-gather (replaces the master's Recv loop, estorch.py:228-233)."""
         if self.n_workers == 1:
             return
         import torch.distributed as dist
-        pl, pb, pairs = self._pairs_local, self._pair_begin, self._pairs
-        dist.all_gather_into_tensor(t[:pairs], t[pb: pb + pl].clone())
-        dist.all_gather_into_tensor(t[pairs:], t[pairs + pb: pairs + pb + pl].clone())
+        W, pl, pb, pairs = self.n_workers, self._pairs_local, self._pair_begin, self._pairs
+        if getattr(self, "_gather_buf", None) is None or self._gather_buf.dtype != t.dtype:
+            self._gather_buf = torch.empty(W, 2, pl, dtype=t.dtype, device=t.device)
+            self._gather_loc = torch.empty(2, pl, dtype=t.dtype, device=t.device)
+        loc = self._gather_loc
+        loc[0].copy_(t[pb: pb + pl])
+        loc[1].copy_(t[pairs + pb: pairs + pb + pl])
+        dist.all_gather_into_tensor(self._gather_buf.view(-1), loc.view(-1))
+        t.view(2, W, pl).copy_(self._gather_buf.permute(1, 0, 2))     # member order: all +, then all -
 
     def _ensure_dist(self):
         if self.n_workers > 1:
@@ -527,7 +540,7 @@ class ES:
         if "_population_parameters" in self.__dict__:
             return self.__dict__["_population_parameters"]
         slot = self._active
-        return LazyPopulation(self._be, slot.theta_prev, self._table, self._offsets_all, self.sigma,
+        return LazyPopulation(self._be, slot.theta_prev, self._table, self._all_offsets(), self.sigma,
                               self.population_size)
 
     @population_parameters.setter

@@ -125,7 +125,7 @@ def test_ns_family_fused_vs_reference_golden(algo, cls):
     assert rel_err(final, g["meta_theta_final"]) < 5e-3
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-3), ("bf16s", 1e-3)])
 def test_north_star_shape_one_generation_properties(precision, tol):
     """BASELINE north-star sizes (P=4096, n=1,001,760, B=256): one fused generation;
     ranks are a permutation, theta moved by ~lr everywhere, returns finite/unique."""
