@@ -57,6 +57,8 @@ SIGNATURES = {
     "estk_eval_mlp_bf16s": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _P, _P, _I32, _F32, _P, _P, _I32,
                             _P, _P, _P, _P, _I32, _I32, _P],
     "estk_eval_mlp_center_bf16s": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _I32, _P, _P, _I32, _I32, _P],
+    "estk_eval_conv_vbn_scratch_bytes": [_P, _I32, _I32],
+    "estk_eval_conv_vbn": [_P, _I32, _P, _P, _P, _P, _I32, _F32, _P, _I32, _P, _P, _I32, _P, _P, _P, _I64, _P],
     "estk_track_best": [_P, _P, _P, _P, _P, _I64, _P],
     "estk_rank_grad_adam": [_P, _P, _P, _F32, _F32, _I32, _P, _P, _P, _I64, _P, _P, _P, _P,
                             C.POINTER(EstkAdamDesc), _P, _P, _P, _P],
@@ -82,7 +84,8 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "estk_last_error" else C.c_int
+        fn.restype = (C.c_char_p if name == "estk_last_error" else
+                      C.c_int64 if name == "estk_eval_conv_vbn_scratch_bytes" else C.c_int)
     _lib = lib
     return lib
 

@@ -28,8 +28,8 @@ class DeviceAgent:
     """Batch-regression agent evaluated by the fused CUDA kernel."""
 
     def __init__(self, obs: torch.Tensor, target: torch.Tensor, bc_obs: int = 0, bc_dim: int = 0):
-        if obs.dim() != 2 or target.dim() != 2 or obs.shape[0] != target.shape[0]:
-            raise ValueError("obs must be [B, in] and target [B, out]")
+        if obs.dim() < 2 or target.dim() != 2 or obs.shape[0] != target.shape[0]:
+            raise ValueError("obs must be [B, in] (or [B, C, H, W] for conv policies) and target [B, out]")
         self.obs = obs.detach().to(torch.float32).contiguous()
         self.target = target.detach().to(torch.float32).contiguous()
         self.bc_obs = int(bc_obs)

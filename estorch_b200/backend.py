@@ -197,6 +197,22 @@ class CudaBackend:
         _capi.check(rc, "estk_eval_mlp_center[" + precision + "]")
         self.launches += 1
 
+    def conv_scratch_bytes(self, ref_batch, B) -> int:
+        return int(self.lib.estk_eval_conv_vbn_scratch_bytes(self._ctx, int(ref_batch), int(B)))
+
+    def eval_conv_vbn(self, n_actions, theta, table, offsets, order, pairs, sigma, xref, obs, target,
+                      ret_plus, ret_minus, scratch):
+        """Conv + VirtualBatchNorm policy (examples/atari.py:14-37); offsets None = centre."""
+        _capi.check(self.lib.estk_eval_conv_vbn(
+            self._ctx, int(n_actions), self._ptr(theta, torch.float32, "theta"),
+            self._ptr(table, torch.float32, "table"), self._ptr(offsets, torch.int64, "offsets"),
+            self._ptr(order, torch.int32, "order"), int(pairs), float(sigma),
+            self._ptr(xref, torch.float32, "xref"), int(xref.shape[0]), self._ptr(obs, torch.float32, "obs"),
+            self._ptr(target, torch.float32, "target"), int(obs.shape[0]),
+            self._ptr(ret_plus, torch.float32, "ret_plus"), self._ptr(ret_minus, torch.float32, "ret_minus"),
+            self._ptr(scratch, torch.uint8, "scratch"), scratch.numel(), self._stream()), "estk_eval_conv_vbn")
+        self.launches += 1
+
     def track_best(self, state, reward, theta, best_theta):
         _capi.check(self.lib.estk_track_best(
             self._ctx, self._ptr(state, torch.uint8, "state"), self._ptr(reward, torch.float32, "reward"),

@@ -37,7 +37,7 @@ import torch
 
 from .agents import DeviceAgent
 from .backend import adam_desc, new_state, read_state, write_state
-from .policy_spec import mlp_spec_from_module
+from .policy_spec import ConvVBNSpec, conv_vbn_spec_from_module, mlp_spec_from_module
 from .population import LazyPopulation, NoiseHandle
 
 __all__ = ["ES", "NS_ES", "NSR_ES", "NSRA_ES", "rank_transformation"]
@@ -207,13 +207,16 @@ class ES:
         self.target = policy(**policy_kwargs).to(self.device)       # estorch.py:142
         parameters = torch.nn.utils.parameters_to_vector(self.target.parameters())
         self.n_parameters = parameters.shape[0]
-        self._spec = mlp_spec_from_module(self.target)
+        self._spec = mlp_spec_from_module(self.target) or conv_vbn_spec_from_module(self.target)
+        self._is_conv = isinstance(self._spec, ConvVBNSpec)
         self._fused = self._decide_fused(optimizer)
         self._host_cache = {}
         if eval_precision not in ("auto", "fp32", "bf16", "bf16s"):
             raise ValueError("eval_precision must be 'auto', 'fp32', 'bf16' or 'bf16s'")
         self._precision = "fp32"
-        if self._fused and eval_precision != "fp32":
+        if self._fused and self._is_conv and eval_precision not in ("auto", "fp32"):
+            raise ValueError("the conv + VirtualBatchNorm evaluate kernel is fp32 only")
+        if self._fused and not self._is_conv and eval_precision != "fp32":
             supported = getattr(self._be, "eval_supports_bf16", lambda d, b: False)(
                 self._spec.dims, self.agent.obs.shape[0])
             if eval_precision in ("bf16", "bf16s") and not supported:
@@ -252,6 +255,12 @@ class ES:
             self._obs = self.agent.obs.to(self._dev).contiguous()
             self._tgt = self.agent.target.to(self._dev).contiguous()
 
+        self._xref = self._conv_scratch = None
+        if self._fused and self._is_conv:
+            self._xref = self.target.xref.detach().to(self._dev, torch.float32).contiguous()
+            nbytes = be.conv_scratch_bytes(self._xref.shape[0], self._obs.shape[0])
+            self._conv_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self._dev)
+
         self._slots = []
         if self._ALGORITHM_TYPE == _Algorithm.classic:
             self.policy = self._make_module()                       # estorch.py:136
@@ -276,7 +285,13 @@ class ES:
         kw = self._optimizer_kwargs
         if kw.get("amsgrad") or kw.get("maximize") or kw.get("differentiable"):
             return False
-        if tuple(self.agent.obs.shape[1:]) != (self._spec.dims[0],) or \
+        if self._is_conv:
+            if self._ALGORITHM_TYPE != _Algorithm.classic:      # no behaviour characteristic on the conv kernel yet
+                return False
+            if tuple(self.agent.obs.shape[1:]) != (4, 84, 84) or \
+                    tuple(self.agent.target.shape[1:]) != (self._spec.n_actions,):
+                return False
+        elif tuple(self.agent.obs.shape[1:]) != (self._spec.dims[0],) or \
                 tuple(self.agent.target.shape[1:]) != (self._spec.dims[-1],):
             return False
         hooks = ("_sample_policy", "_calculate_grad", "_calculate_returns", "_after_optimize",
@@ -512,14 +527,19 @@ class ES:
     def _fused_generation(self, slot):
         """One generation, entirely on the device (no host synchronisation)."""
         be, P, pairs, pl, pb = self._be, self.population_size, self._pairs, self._pairs_local, self._pair_begin
-        dims = self._spec.dims
+        dims = None if self._is_conv else self._spec.dims
         self._upload_batch()
         slot.theta_prev.copy_(slot.theta)
         self._draw_offsets()
         R = self._returns
-        be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
-                    self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
-                    **self._eval_kw(slot))
+        if self._is_conv:
+            be.eval_conv_vbn(self._spec.n_actions, slot.theta, self._table, self._offsets, self._order, pl,
+                             self.sigma, self._xref, self._obs, self._tgt, R[pb: pb + pl],
+                             R[pairs + pb: pairs + pb + pl], self._conv_scratch)
+        else:
+            be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
+                        self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
+                        **self._eval_kw(slot))
         self._all_gather_halves(R)
         ad = self._adam_desc(slot.optimizer)
         if self.n_workers == 1:
@@ -530,7 +550,11 @@ class ES:
                          self.n_parameters, self._grad, self._ranks, None)
             self._all_reduce(self._grad)
             be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
-        be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, **self._eval_kw(slot, True))
+        if self._is_conv:
+            be.eval_conv_vbn(self._spec.n_actions, slot.theta, None, None, None, 1, 0.0, self._xref, self._obs,
+                             self._tgt, self._episode, None, self._conv_scratch)
+        else:
+            be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, **self._eval_kw(slot, True))
         be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
         self._best_slot = slot
 

@@ -168,6 +168,21 @@ ESTK_API int estk_eval_mlp_center_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc
                                float* return_out, float* bc_out, int32_t bc_obs, int32_t bc_dim,
                                void* stream);
 
+/* ---- conv + VirtualBatchNorm policy of examples/atari.py:14-37 (BASELINE config 5):
+ * conv1 4->16 k8 s4, VBN(16), ReLU, conv2 16->32 k4 s2, VBN(32), ReLU, fc1 2592->256,
+ * ReLU, fc2 256->n_actions; VBN statistics = per-(C,H,W) mean / unbiased variance of
+ * the reference batch xref [ref_batch,4,84,84] under the member's own weights
+ * (estorch/modules.py:48-58).  obs [B,4,84,84], target [B,n_actions]; return =
+ * -mean((policy(obs)-target)^2).  offsets == NULL evaluates theta itself into
+ * returns_plus[0].  scratch: caller-owned device slab of at least
+ * estk_eval_conv_vbn_scratch_bytes(ctx, ref_batch, B) bytes.  fp32 throughout. */
+ESTK_API int64_t estk_eval_conv_vbn_scratch_bytes(estk_ctx* ctx, int32_t ref_batch, int32_t B);
+ESTK_API int estk_eval_conv_vbn(estk_ctx* ctx, int32_t n_actions, const float* theta, const float* table,
+                       const int64_t* offsets, const int32_t* order, int32_t pairs, float sigma,
+                       const float* xref, int32_t ref_batch, const float* obs, const float* target,
+                       int32_t B, float* returns_plus, float* returns_minus, void* scratch,
+                       int64_t scratch_bytes, void* stream);
+
 /* Unperturbed policy (estorch.py:181-182 `_after_optimize` rollout):
  * return_out[0] = return of theta; bc_out (nullable) [bc_dim]. */
 ESTK_API int estk_eval_mlp_center(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,

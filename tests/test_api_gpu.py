@@ -160,3 +160,66 @@ def test_north_star_shape_one_generation_properties(precision, tol):
         row = pop[member].cpu().numpy()
         want = orc.synthetic_return(orc.mlp_forward(row, dims, obs.numpy()), tgt.numpy())
         assert abs(ret[member] - float(want)) < tol * abs(float(want))
+
+
+class AtariPolicy(torch.nn.Module):
+    """Architecture of the reference's examples/atari.py:14-37, built with estorch_b200's VirtualBatchNorm."""
+    def __init__(self, n_actions, xref):
+        super().__init__()
+        self.xref = xref
+        self.conv1 = torch.nn.Conv2d(4, 16, 8, 4)
+        self.bn1 = E.VirtualBatchNorm(16)
+        self.conv2 = torch.nn.Conv2d(16, 32, 4, 2)
+        self.bn2 = E.VirtualBatchNorm(32)
+        self.fc1 = torch.nn.Linear(2592, 256)
+        self.fc2 = torch.nn.Linear(256, n_actions)
+
+    def forward(self, x):
+        F = torch.nn.functional
+        xref = F.relu(self.bn1(self.conv1(self.xref.to(x.device))))
+        xref = F.relu(self.bn2(self.conv2(xref)))
+        x = F.relu(self.bn1(self.conv1(x)))
+        x = F.relu(self.bn2(self.conv2(x)))
+        return self.fc2(F.relu(self.fc1(x.view(-1, 2592))))
+
+
+def test_conv_vbn_policy_fused_generation_vs_oracle():
+    """BASELINE config 5 shape (Atari conv + VirtualBatchNorm), small sizes: one fused generation;
+    returns vs the oracle's atari_forward, ranks / gradient / Adam vs the oracle on the same return bits."""
+    g = torch.Generator().manual_seed(5)
+    xref = torch.rand(8, 4, 84, 84, generator=g)
+    obs, tgt = torch.rand(4, 4, 84, 84, generator=g), torch.randn(4, 4, generator=g)
+    rec = {}
+
+    class Q(E.ES):
+        def log(self):
+            rec["returns"] = self.population_returns[:, 0].copy()
+            rec["episode"] = self.episode_reward
+    torch.manual_seed(1)
+    P, sigma, table_len, seed = 8, 0.02, 1 << 21, 9
+    es = Q(AtariPolicy, E.DeviceAgent, torch.optim.Adam, population_size=P, sigma=sigma,
+           policy_kwargs=dict(n_actions=4, xref=xref), agent_kwargs=dict(obs=obs, target=tgt),
+           optimizer_kwargs={"lr": 0.01}, noise_table_size=table_len, noise_seed=seed)
+    assert es._fused and es._is_conv and es.n_parameters == 677268
+    theta0 = es._slots[0].theta.cpu().numpy().copy()
+    table = es._table.cpu().numpy()
+    es.train(n_steps=1)
+    n = theta0.size
+    offs = orc.noise_offsets(seed, 0, 0, P // 2, table_len, n)
+    pop, eps = orc.sample_population(theta0, table, offs, sigma)
+    want = np.array([orc.synthetic_return(orc.atari_forward(pop[i], 4, xref.numpy(), obs.numpy()), tgt.numpy())
+                     for i in range(P)])
+    assert rel_err(rec["returns"], want) < 5e-5
+    np.testing.assert_array_equal(es._ranks.cpu().numpy(), orc.compute_ranks(rec["returns"]))
+    grad = orc.calculate_grad(rec["returns"], eps, sigma)
+    assert rel_err(es._grad.cpu().numpy(), grad) < 1e-5
+    th, _, _ = orc.adam_step(theta0, np.zeros(n, np.float32), np.zeros(n, np.float32),
+                             orc.negate_clamp(es._grad.cpu().numpy()), 1)
+    assert rel_err(es._slots[0].theta.cpu().numpy(), th) < 1e-6
+    ep = float(orc.synthetic_return(orc.atari_forward(th, 4, xref.numpy(), obs.numpy()), tgt.numpy()))
+    assert abs(rec["episode"] - ep) < 5e-5 * abs(ep)
+    # the torch module (parameters are views of the flat device theta) agrees with the kernel
+    # (cuDNN convolutions run in TF32 by default, hence the loose 1e-3)
+    with torch.no_grad():
+        out = es.policy(obs.to(es._dev))
+    assert abs(float(-((out - tgt.to(es._dev)) ** 2).mean()) - rec["episode"]) < 1e-3 * abs(ep)

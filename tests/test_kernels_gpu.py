@@ -442,3 +442,33 @@ def test_eval_mlp_bf16s_shadow_sources(be, dims, B, pairs):
         idx += dims[i + 1]
     want = float(orc.synthetic_return(orc.mlp_forward_bf16(crow, dims, obs), tgt))
     assert abs(float(one) - want) < 5e-4 * abs(want)
+
+
+# ------------------------------------------------------------------ conv + VirtualBatchNorm evaluate
+def test_eval_conv_vbn_matches_oracle_and_reference_golden(be):
+    """examples/atari.py policy: (1) the centre evaluation reproduces the logits-based
+    return of the reference's own forward (golden), (2) perturbed members match the oracle."""
+    g = load_golden("atari_forward.npz")
+    theta = g["theta16"].astype(np.float32)
+    xref = g["xref8"].astype(np.float32) / np.float32(255)
+    x = g["x8"].astype(np.float32) / np.float32(255)
+    A, R, B = 4, xref.shape[0], x.shape[0]
+    rng = np.random.RandomState(3)
+    tgt = rng.standard_normal((B, A)).astype(np.float32)
+    scratch = torch.empty(be.conv_scratch_bytes(R, B), dtype=torch.uint8, device=be.device)
+    one = be.zeros(1)
+    be.eval_conv_vbn(A, dev(be, theta), None, None, None, 1, 0.0, dev(be, xref), dev(be, x), dev(be, tgt),
+                     one, None, scratch)
+    want = float(orc.synthetic_return(g["logits"], tgt))          # logits from the unmodified reference
+    assert abs(float(one) - want) < 2e-5 * abs(want)
+    n = theta.size
+    pairs = 3
+    table_len = (n + 31) // 32 * 32 + (1 << 12)
+    table = rng.standard_normal(table_len).astype(np.float32)
+    offs = orc.noise_offsets(5, 0, 0, pairs, table_len, n)
+    ret = be.zeros(2 * pairs)
+    be.eval_conv_vbn(A, dev(be, theta), dev(be, table), dev(be, offs), None, pairs, 0.02, dev(be, xref),
+                     dev(be, x), dev(be, tgt), ret[:pairs], ret[pairs:], scratch)
+    pop, _ = orc.sample_population(theta, table, offs, 0.02)
+    want = np.array([orc.synthetic_return(orc.atari_forward(pop[i], A, xref, x), tgt) for i in range(2 * pairs)])
+    assert rel_err(ret.cpu().numpy(), want) < 5e-5
