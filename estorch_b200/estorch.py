@@ -268,6 +268,7 @@ class ES:
             self._slots.append(_PolicySlot(self.policy, self.optimizer, be, self._fused))
         self._active = self._slots[0] if self._slots else None
         self.step = 0
+        self._generation = 0     # total generations ever run: indexes the noise offsets (never reset)
 
     # ------------------------------------------------------------------ setup helpers
     def _make_module(self):
@@ -425,10 +426,10 @@ class ES:
 
     def _draw_offsets(self):
         be = self._be
-        self._offsets_gen = self.step
-        be.make_offsets(self._noise_seed, None, self.step, self._pair_begin, self._pairs_local,
+        self._offsets_gen = self._generation
+        be.make_offsets(self._noise_seed, None, self._generation, self._pair_begin, self._pairs_local,
                         self._table.numel(), self.n_parameters, self._offsets, self._order)
-        self._offsets_all_gen = self.step if self.n_workers == 1 else None
+        self._offsets_all_gen = self._generation if self.n_workers == 1 else None
 
     def _all_offsets(self):
         """Offsets of ALL pairs of the last sampled population (lazy population rows);
@@ -518,7 +519,7 @@ class ES:
         return kw
 
     def _upload_batch(self):
-        nb = self.agent.next_batch(self.step)
+        nb = self.agent.next_batch(self._generation)
         if nb is not None:
             obs, tgt = nb
             self._obs.copy_(obs, non_blocking=True)
@@ -638,6 +639,7 @@ class ES:
                         self.log()
                     self._sync_stop()
                 self.step += 1
+                self._generation += 1
         if self._fused:
             for s in self._slots:
                 s.mirror_adam_state()
@@ -679,6 +681,71 @@ class ES:
             elif self.n_workers != n_proc:
                 raise RuntimeError(f"train(n_proc={n_proc}) but the launcher started {self.n_workers} processes")
         self._master()
+
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    # (the reference keeps everything in memory only; users pickle from log())
+    def state_dict(self):
+        """Everything needed to continue training bit-identically: theta / Adam moments /
+        step counters / best snapshot per (policy, optimizer) slot, the generation
+        counter and noise seed (the table is regenerated from the seed), and the host
+        scalars of the algorithm."""
+        self._host_cache = {}
+        slots = []
+        for s_ in self._slots:
+            s_.push_theta()
+            st = read_state(s_.state)
+            slots.append({"theta": s_.theta.detach().cpu().clone(), "m": s_.m.detach().cpu().clone(),
+                          "v": s_.v.detach().cpu().clone(), "best_theta": s_.best_theta.detach().cpu().clone(),
+                          "state": st,
+                          "optimizer": None if s_.flattened else copy.deepcopy(s_.optimizer.state_dict())})
+        out = {"version": 1, "algorithm": type(self).__name__, "n_parameters": self.n_parameters,
+               "population_size": self.population_size, "sigma": self.sigma, "noise_seed": self._noise_seed,
+               "noise_table_size": self._table.numel(), "generation": self._generation, "slots": slots,
+               "best_reward": self.best_reward, "numpy_rng": np.random.get_state()}
+        for k in ("_archive", "idx", "weight", "t", "_best_host"):
+            if hasattr(self, k):
+                out[k] = copy.deepcopy(getattr(self, k))
+        if "_best_policy_dict" in self.__dict__:
+            out["best_policy_dict"] = {k: v.detach().cpu().clone() for k, v in self.__dict__["_best_policy_dict"].items()}
+        return out
+
+    def load_state_dict(self, sd):
+        if sd.get("algorithm") != type(self).__name__ or sd["n_parameters"] != self.n_parameters or \
+                sd["population_size"] != self.population_size or len(sd["slots"]) != len(self._slots):
+            raise ValueError("checkpoint does not match this algorithm / policy / population")
+        if sd["noise_seed"] != self._noise_seed or sd["noise_table_size"] != self._table.numel():
+            raise ValueError("checkpoint was written with a different noise table (seed or size)")
+        self.sigma = sd["sigma"]
+        self._generation = int(sd["generation"])
+        for s_, rec in zip(self._slots, sd["slots"]):
+            s_.ensure_flat()
+            s_.theta.copy_(rec["theta"]); s_.m.copy_(rec["m"]); s_.v.copy_(rec["v"])
+            s_.best_theta.copy_(rec["best_theta"])
+            write_state(s_.state, **rec["state"])
+            if not s_.flattened:
+                torch.nn.utils.vector_to_parameters(rec["theta"].to(next(s_.module.parameters()).device).clone(),
+                                                    s_.module.parameters())
+                if rec["optimizer"] is not None:
+                    s_.optimizer.load_state_dict(rec["optimizer"])
+            else:
+                s_.mirror_adam_state()
+        for k in ("_archive", "idx", "weight", "t", "_best_host"):
+            if k in sd:
+                setattr(self, k, copy.deepcopy(sd[k]))
+        if not self._fused or self._ALGORITHM_TYPE == _Algorithm.novelty:
+            self.best_reward = sd["best_reward"]
+        if "best_policy_dict" in sd:
+            self.best_policy_dict = {k: v.clone() for k, v in sd["best_policy_dict"].items()}
+        np.random.set_state(sd["numpy_rng"])
+        self._host_cache = {}
+
+    def save_checkpoint(self, path):
+        if self.rank == 0:
+            torch.save(self.state_dict(), path)
+
+    def load_checkpoint(self, path):
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
 
 
 class NS_ES(ES):

@@ -292,3 +292,38 @@ def test_virtual_batch_norm_matches_reference_golden():
     np.testing.assert_allclose(y_ref.numpy(), g["y_ref"], rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-6, atol=1e-6)
     assert sorted(vbn.state_dict().keys()) == ["bias", "weight"]   # stats are not in state_dict
+
+
+@pytest.mark.parametrize("algo", ["es", "nsra"])
+def test_checkpoint_resume_is_bit_identical(algo, tmp_path):
+    """train(2) + save + train(2)  ==  fresh instance + load + train(2)."""
+    g = load_golden("es_cartpole_p64.npz" if algo == "es" else "nsra_bipedal_p32.npz")
+
+    def make():
+        np.random.seed(7)
+        torch.manual_seed(3)
+        if algo == "es":
+            es = _make(E.ES, g, 64, 0.1)
+        else:
+            es = _make(E.NSRA_ES, g, 32, 0.02, weight_t=2)
+        es.log = lambda: None
+        return es
+    a = make()
+    a.train(n_steps=2)
+    path = str(tmp_path / "ck.pt")
+    a.save_checkpoint(path)
+    a.train(n_steps=2)
+    b = make()
+    b.load_checkpoint(path)
+    assert b._generation == 2
+    b.train(n_steps=2)
+    for sa, sb in zip(a._slots, b._slots):
+        np.testing.assert_array_equal(sa.theta.numpy(), sb.theta.numpy())
+        np.testing.assert_array_equal(sa.m.numpy(), sb.m.numpy())
+        np.testing.assert_array_equal(sa.v.numpy(), sb.v.numpy())
+    assert a.best_reward == b.best_reward and a._generation == b._generation == 4
+    if algo == "nsra":
+        assert a.weight == b.weight and a.t == b.t and len(a._archive) == len(b._archive)
+        np.testing.assert_array_equal(np.stack(a._archive), np.stack(b._archive))
+    # a second train() call continues with NEW noise (generation counter is not reset)
+    assert a.step == 2
