@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       d.ep16 = cached_trow16 + rbase;
       d.K = K;
       d.sub_items = rows * 8;                                  // 16-byte output chunks per k-block
-      d.n_items = d.sub_items * min(kSubPerStage, K / kBlockK - kb);
+      d.n_items = (kSubPerStage > 1) ? d.sub_items * min(kSubPerStage, K / kBlockK - kb) : d.sub_items;
       d.ssig = cached_ssig;
     };
     auto advance = [&](int& task, int& l, int& n0, int& kb) -> bool {
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           for (int u = 0; u < 8; ++u) {
             const int it = it0 + u * kPT + ptid;
             if (it < cur.n_items && !(p.dbg & 1)) {
-              const int sub = it >= cur.sub_items, iq = it - sub * cur.sub_items;
+              const int sub = (kSubPerStage > 1) ? (it >= cur.sub_items) : 0, iq = it - sub * cur.sub_items;
               const int64_t off = (int64_t)(iq >> 3) * cur.K + sub * kBlockK + (iq & 7) * 8;
               t16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.th16 + off));
               e16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.ep16 + off));
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(w[c]) : "r"(sg2), "r"(ew[c]), "r"(tw[c]));
-              const int sub = it >= cur.sub_items, iq = it - sub * cur.sub_items;
+              const int sub = (kSubPerStage > 1) ? (it >= cur.sub_items) : 0, iq = it - sub * cur.sub_items;
               st_shared_v4(sbase + sub * kKBlockBytes + sw128_offset(iq >> 3, iq & 7), w[0], w[1], w[2], w[3]);
             }
           }
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           for (int u = 0; u < 4; ++u) {
             const int it = it0 + u * kPT + ptid;
             if (it < cur.n_items && !(p.dbg & 1)) {
-              const int sub = it >= cur.sub_items, iq = it - sub * cur.sub_items;
+              const int sub = (kSubPerStage > 1) ? (it >= cur.sub_items) : 0, iq = it - sub * cur.sub_items;
               const int64_t off = (int64_t)(iq >> 3) * cur.K + sub * kBlockK + (iq & 7) * 8;
               th[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off));
               th[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off + 4));
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
               const uint32_t w1 = pack_bf16(fmaf(sg, ep[u][0].z, th[u][0].z), fmaf(sg, ep[u][0].w, th[u][0].w));
               const uint32_t w2 = pack_bf16(fmaf(sg, ep[u][1].x, th[u][1].x), fmaf(sg, ep[u][1].y, th[u][1].y));
               const uint32_t w3 = pack_bf16(fmaf(sg, ep[u][1].z, th[u][1].z), fmaf(sg, ep[u][1].w, th[u][1].w));
-              const int sub = it >= cur.sub_items, iq = it - sub * cur.sub_items;
+              const int sub = (kSubPerStage > 1) ? (it >= cur.sub_items) : 0, iq = it - sub * cur.sub_items;
               st_shared_v4(sbase + sub * kKBlockBytes + sw128_offset(iq >> 3, iq & 7), w0, w1, w2, w3);
             }
           }
