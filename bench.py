@@ -284,6 +284,12 @@ def run_ours(args, wl, rank, world, local_rank):
               "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": flops_eval / t_eval / 1e9 / peaks["tensor"],
               "ms": t_eval, "traffic": None, "algorithmic_bytes": bytes_eval, "flops": flops_eval,
               "hbm_frac_of_noise_stream": bytes_eval / t_eval / 1e6 / peaks["hbm"]}
+    # DRAM traffic per launch from the committed `ncu --set full` capture of exactly these
+    # kernels / shapes on one GPU (profiles/r01_ncu_full_summary.txt); null elsewhere
+    if args.workload == "north_star" and world == 1:
+        k_grad["traffic"] = 2.103511e9 + 6.6e6
+        if es._precision == "bf16s":
+            k_eval["traffic"] = 0.557642e9 + 3.4e6
     dominant = k_eval if t_eval >= t_grad else k_grad
     roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = dominant["kernel"]
