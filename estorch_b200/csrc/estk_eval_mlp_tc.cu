@@ -69,7 +69,7 @@ struct EvalTCParams {
   unsigned int* counters;  // [pairs*2]
   int n_tasks;             // pairs * n_signs * chunks
   int n_signs;             // 2, or 1 for the centre evaluation
-  int dbg;                 // ESTK_TC_DEBUG bit mask (perf triage only): 1 no producer loads, 2 no epilogue work, 4 no MMA
+  int dbg;                 // ESTK_TC_DEBUG bit mask (perf triage only): 1 no producer loads, 4 no MMA, 8 role counters, 16 TMEM read only
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           __syncwarp();
           if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h), 0);
         };
-        for (int c0 = 0; c0 < N && !(p.dbg & 2); c0 += 32) {
+        for (int c0 = 0; c0 < N; c0 += 32) {
           if (!last && c0 == 256) hand_over();
           uint32_t va[32];
           const long long tl0 = eprof ? clock64() : 0ll;
