@@ -6,7 +6,7 @@ docs/index.rst:4-15): ``ES``, ``NS_ES``, ``NSR_ES``, ``NSRA_ES``,
 """
 from .agents import DeviceAgent, SyntheticAgent
 from .estorch import ES, NS_ES, NSR_ES, NSRA_ES, rank_transformation
-from .modules import VirtualBatchNorm
+from .vbn import VirtualBatchNorm
 
 __version__ = "0.1.0"
 __all__ = ["ES", "NS_ES", "NSR_ES", "NSRA_ES", "rank_transformation", "VirtualBatchNorm",

@@ -93,7 +93,7 @@ def conv_vbn_spec_from_module(module: nn.Module) -> Optional[ConvVBNSpec]:
     Conv2d(4,16,8,4) / VirtualBatchNorm(16) / Conv2d(16,32,4,2) / VirtualBatchNorm(32) /
     Linear(2592,256) / Linear(256,A), plus an ``xref`` tensor ``[R,4,84,84]``; the forward
     is probed against the same chain evaluated from the module's own parameters."""
-    from .modules import VirtualBatchNorm
+    from .vbn import VirtualBatchNorm
     leaves = _leaf_modules(module)
     if len(leaves) != 6:
         return None
