@@ -16,8 +16,9 @@
 //            bit-exact integer ranks; stable-by-index on ties), centres in
 //            fp64 -> fp32 and blends reward/novelty rows          -> grid.sync
 //   phase B  CTA (cs, ps) owns float4 columns [c0,c1) and sorted pair slots
-//            [s0,s1): 128-bit read-only loads, fp32 FMA into registers, 8
-//            independent loads in flight per thread.  With PS == 1 every CTA
+//            [s0,s1): 128-bit read-only loads, fp32 FMA into registers, 16
+//            independent loads in flight per thread (128 KB per SM: the kernel is
+//            latency-bound at the L2, bytes in flight set its rate).  With PS == 1 every CTA
 //            walks all pairs in the same (offset-sorted) order, so rows that
 //            overlap in the table are served from L2 instead of HBM.
 //   phase C  PS == 1: epilogue straight from registers.  PS > 1: partial sums
@@ -25,11 +26,11 @@
 //            (deterministic; no atomics anywhere).
 #include "estk_common.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr int kPairTile = 256;  // pair weights / offsets staged per shared-memory refill
 
 struct RankGradParams {
@@ -122,8 +123,9 @@ __device__ __forceinline__ void epilogue(const RankGradParams& p, const AdamScal
   }
 }
 
-template <int NC>
-__global__ void __launch_bounds__(kThreads) rank_grad_kernel(const RankGradParams p) {
+template <int NC, int T, int LOADS = 8>
+__global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
+  constexpr int kThreads = T;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) rank_grad_kernel(const RankGradParam
         s_off4[t] = (uint32_t)(p.offsets[jl] >> 2);
       }
       __syncthreads();
-      constexpr int U = 8 / NC;  // 8 independent 16-byte loads in flight per thread
+      constexpr int U = LOADS / NC;  // LOADS independent 16-byte loads in flight per thread
       int jj = 0;
       for (; jj + U <= cnt; jj += U) {
         float4 t[U][NC];
@@ -328,15 +330,16 @@ __global__ void __launch_bounds__(256) clamp_adam_kernel(const RankGradParams p)
 // of clamp_adam_kernel can observe the incremented value.
 __global__ void bump_adam_step_kernel(estk_state* state) { state->adam_step += 1; }
 
-template <int NC>
+template <int NC, int T, int LOADS = 8>
 int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
+  constexpr int kThreads = T;
   int occ = 0;
-  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC>, kThreads, 0));
+  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC, T, LOADS>, kThreads, 0));
   if (occ < 1) {
     estk_set_error("rank_grad_kernel<%d> cannot be resident", NC);
     return ESTK_ERR_CUDA;
   }
-  if (occ > 4) occ = 4;  // 4 x 256 threads x 8 x 16 B in flight per SM saturates HBM
+  if (occ > 1024 / kThreads) occ = 1024 / kThreads;  // <= 1024 threads x 8 x 16 B in flight per SM
   const int gmax = occ * ctx->sm_count;
   const int64_t n4 = p.n4;
   if (n4 >= (int64_t)ctx->sm_count * 512) {
@@ -357,7 +360,7 @@ int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   }
   const int grid = p.CS * p.PS;
   void* args[] = {(void*)&p};
-  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC>, dim3(grid), dim3(kThreads), args, 0, stream));
+  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC, T, LOADS>, dim3(grid), dim3(kThreads), args, 0, stream));
   return ESTK_OK;
 }
 
@@ -372,10 +375,19 @@ int check_common(estk_ctx* ctx, const float* returns, int P, const float* table,
 }
 
 int dispatch(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
-  // NC = float4 columns per thread per pass; only matters when PS == 1
-  const int64_t per_cta = p.n4 / ((int64_t)ctx->sm_count * 4) + 1;
-  if (per_cta > kThreads) return launch_rank_grad<2>(ctx, p, stream);
-  return launch_rank_grad<1>(ctx, p, stream);
+  // Large n: 512-thread CTAs, four float4 columns per thread (one CTA per SM), so that a CTA
+  // covers its whole column slice in ONE pass over the (offset-sorted) pair list -- all CTAs then
+  // walk the table in lock-step, which is what makes overlapping rows hit L2.
+  const char* force = getenv("ESTK_RG_VARIANT");            // perf triage only
+  const int variant = force ? atoi(force) : 0;
+  if (p.n4 >= (int64_t)ctx->sm_count * 512) {
+    if (variant == 1) return launch_rank_grad<2, 256>(ctx, p, stream);
+    if (variant == 2) return launch_rank_grad<2, 512>(ctx, p, stream);
+    if (variant == 3) return launch_rank_grad<4, 512, 8>(ctx, p, stream);
+    if (variant == 4) return launch_rank_grad<4, 384, 24>(ctx, p, stream);
+    return launch_rank_grad<4, 512, 16>(ctx, p, stream);   // 16 x 16 B in flight per thread = 128 KB per SM
+  }
+  return launch_rank_grad<1, 256>(ctx, p, stream);
 }
 
 }  // namespace

@@ -497,6 +497,8 @@ class ES:
             if not dist.is_initialized():
                 backend = "nccl" if self._dev.type == "cuda" else "gloo"
                 dist.init_process_group(backend=backend)
+                import atexit
+                atexit.register(lambda: dist.is_initialized() and dist.destroy_process_group())
 
     # ------------------------------------------------------------------ fused generation
     def _adam_desc(self, optimizer):
