@@ -327,3 +327,49 @@ def test_checkpoint_resume_is_bit_identical(algo, tmp_path):
         np.testing.assert_array_equal(np.stack(a._archive), np.stack(b._archive))
     # a second train() call continues with NEW noise (generation counter is not reset)
     assert a.step == 2
+
+
+def test_lazy_population_indexing_and_noise_handle():
+    g = load_golden("es_cartpole_p64.npz")
+    es = _make(E.ES, g, 64, 0.1)
+    es.log = lambda: None
+    _load_theta(es.policy, g["theta0"])
+    es.train(n_steps=1)
+    pop = es.population_parameters
+    assert len(pop) == 64 and pop.shape == (64, 4610) and pop.size(1) == 4610
+    full = pop.materialize()
+    assert full.shape == (64, 4610)
+    np.testing.assert_array_equal(pop[3].numpy(), full[3].numpy())
+    np.testing.assert_array_equal(pop[-1].numpy(), full[63].numpy())
+    np.testing.assert_array_equal(pop[10:13].numpy(), full[10:13].numpy())
+    np.testing.assert_array_equal(pop[[1, 40]].numpy(), full[[1, 40]].numpy())
+    np.testing.assert_array_equal(pop[torch.tensor(7)].numpy(), full[7].numpy())
+    with pytest.raises(IndexError):
+        pop[64]
+    # mirrored layout of estorch.py:192: row j+P/2 = 2*theta - row j
+    theta = g["theta_before"][0]
+    assert rel_err((full[5] + full[5 + 32]).numpy() / 2, theta) < 1e-6
+
+
+def test_checkpoint_resume_hooks_mode(tmp_path):
+    g = load_golden("es_cartpole_p64.npz")
+    obs, tgt = torch.from_numpy(g["obs"]), torch.from_numpy(g["target"])
+
+    def make():
+        torch.manual_seed(3)
+        es = E.ES(MLP, HostAgent, torch.optim.SGD, population_size=16, sigma=0.1,
+                  policy_kwargs={"dims": [4, 64, 64, 2]}, agent_kwargs=dict(obs=obs, target=tgt),
+                  optimizer_kwargs={"lr": 0.05, "momentum": 0.9}, noise_table_size=1 << 15, _backend=OracleBackend())
+        es.log = lambda: None
+        return es
+    a = make()
+    a.train(n_steps=2)
+    a.save_checkpoint(str(tmp_path / "h.pt"))
+    a.train(n_steps=2)
+    b = make()
+    b.load_checkpoint(str(tmp_path / "h.pt"))
+    b.train(n_steps=2)
+    ta = torch.nn.utils.parameters_to_vector(a.policy.parameters()).detach().numpy()
+    tb = torch.nn.utils.parameters_to_vector(b.policy.parameters()).detach().numpy()
+    np.testing.assert_array_equal(ta, tb)             # incl. the SGD momentum buffers restored
+    assert a.best_reward == b.best_reward

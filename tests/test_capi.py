@@ -57,3 +57,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_error_reporting_through_the_c_abi_without_gpu():
+    """estk_ctx_create on a box without a usable device returns a negative status and leaves a
+    message in estk_last_error(); null arguments are rejected before any CUDA call."""
+    import ctypes as C
+    import torch
+    from estorch_b200 import _capi
+    lib = _capi.load()
+    assert lib.estk_ctx_create(0, None) == -1                       # ESTK_ERR_INVALID
+    assert b"null" in lib.estk_last_error()
+    if not torch.cuda.is_available():
+        ctx = C.c_void_p()
+        rc = lib.estk_ctx_create(0, C.byref(ctx))
+        assert rc < 0 and len(lib.estk_last_error()) > 0 and not ctx.value
+    assert lib.estk_ctx_destroy(None) == 0
+    assert lib.estk_eval_mlp_bf16_supported(None, 256) == 0
