@@ -50,12 +50,12 @@ SIGNATURES = {
                       _P, _P, _P, _P, _I32, _I32, _P],
     "estk_eval_mlp_center": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _I32, _P, _P, _I32, _I32, _P],
     "estk_eval_mlp_bf16": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _I32, _F32, _P, _P, _I32,
-                           _P, _P, _P, _P, _I32, _I32, _P],
+                           _P, _P, _P, _P, _I32, _I32, _P, _P],
     "estk_eval_mlp_center_bf16": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _I32, _P, _P, _I32, _I32, _P],
     "estk_eval_mlp_bf16_supported": [C.POINTER(EstkMlpDesc), _I32],
     "estk_shadow_bf16": [_P, _P, _P, _I64, _P],
     "estk_eval_mlp_bf16s": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _P, _P, _I32, _F32, _P, _P, _I32,
-                            _P, _P, _P, _P, _I32, _I32, _P],
+                            _P, _P, _P, _P, _I32, _I32, _P, _P],
     "estk_eval_mlp_center_bf16s": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _I32, _P, _P, _I32, _I32, _P],
     "estk_eval_conv_vbn_scratch_bytes": [_P, _I32, _I32],
     "estk_eval_conv_vbn": [_P, _I32, _P, _P, _P, _P, _I32, _F32, _P, _I32, _P, _P, _I32, _P, _P, _P, _I64, _P],

@@ -156,7 +156,7 @@ class CudaBackend:
 
     def eval_mlp(self, dims, theta, table, offsets, order, pairs, sigma, obs, target,
                  ret_plus, ret_minus, bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32",
-                 theta16=None, table16=None):
+                 theta16=None, table16=None, centre_out=None):
         d = mlp_desc(dims)
         if obs.shape != (obs.shape[0], dims[0]) or target.shape != (obs.shape[0], dims[-1]):
             raise ValueError(f"obs {tuple(obs.shape)} / target {tuple(target.shape)} do not match dims {list(dims)}")
@@ -164,7 +164,13 @@ class CudaBackend:
                   float(sigma), self._ptr(obs, torch.float32, "obs"), self._ptr(target, torch.float32, "target"),
                   int(obs.shape[0]), self._ptr(ret_plus, torch.float32, "ret_plus"),
                   self._ptr(ret_minus, torch.float32, "ret_minus"), self._ptr(bc_plus, torch.float32, "bc_plus"),
-                  self._ptr(bc_minus, torch.float32, "bc_minus"), int(bc_obs), int(bc_dim), self._stream())
+                  self._ptr(bc_minus, torch.float32, "bc_minus"), int(bc_obs), int(bc_dim))
+        stream = (self._stream(),)
+        if precision in ("bf16", "bf16s"):
+            stream = (self._ptr(centre_out, torch.float32, "centre_out"), self._stream())
+        elif centre_out is not None:
+            raise ValueError("centre_out (folded post-update rollout) needs a tensor-core precision mode")
+        common = common + stream
         th, tb = self._ptr(theta, torch.float32, "theta"), self._ptr(table, torch.float32, "table")
         if precision == "bf16s":
             if theta16 is None or table16 is None:

@@ -67,7 +67,9 @@ struct EvalTCParams {
   int bc_obs, bc_dim;
   float* partial;          // [pairs*2][chunks*CG]
   unsigned int* counters;  // [pairs*2]
-  int n_tasks;             // pairs * n_signs * chunks
+  float* centre_out;       // optional: also evaluate theta itself (sigma = 0) into centre_out[0]
+  int n_centre;            // number of leading centre tasks (0 or chunks)
+  int n_tasks;             // n_centre + pairs * n_signs * chunks
   int n_signs;             // 2, or 1 for the centre evaluation
   int dbg;                 // ESTK_TC_DEBUG bit mask (perf triage only): 1 no producer loads, 4 no MMA, 8 role counters, 16 TMEM read only
 };
@@ -246,6 +248,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 }
 
 struct Layer { int K, N; int64_t wbase, bbase; };
+
+// task -> (slot, sign, chunk); the first n_centre tasks evaluate theta itself
+struct TaskId { int slot, sgn, chunk; bool centre; };
+__device__ __forceinline__ TaskId decode_task(const EvalTCParams& p, int task, bool all_centre) {
+  TaskId t;
+  if (task < p.n_centre) { t.slot = 0; t.sgn = 0; t.chunk = task; t.centre = true; return t; }
+  const int q = task - p.n_centre;
+  t.chunk = q % p.chunks;
+  t.sgn = (q / p.chunks) % p.n_signs;
+  t.slot = q / (p.chunks * p.n_signs);
+  t.centre = all_centre;
+  return t;
+}
 #define PROF_ON (prof)
 #define PROF_T() (PROF_ON ? clock64() : 0ll)
 #define PROF_ADD(i, t0) do { if (PROF_ON) atomicAdd(&g_tc_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
@@ -373,12 +388,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     const long long te0 = eprof ? clock64() : 0ll;
     for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
       const long long to0 = eprof ? clock64() : 0ll;
-      const int chunk = task % p.chunks;
-      const int sgn = (task / p.chunks) % p.n_signs;
-      const int slot = task / (p.chunks * p.n_signs);
-      const int j = p.order ? p.order[slot] : slot;
-      const float* trow = centre ? p.theta : p.table + p.offsets[j];
-      const float ssig = centre ? 0.f : (sgn ? -p.sigma : p.sigma);
+      const TaskId tk = decode_task(p, task, centre);
+      const int chunk = tk.chunk, sgn = tk.sgn, slot = tk.slot;
+      const int j = (!tk.centre && p.order) ? p.order[slot] : slot;
+      const float* trow = tk.centre ? p.theta : p.table + p.offsets[j];
+      const float ssig = tk.centre ? 0.f : (sgn ? -p.sigma : p.sigma);
       const int b = (chunk * CG + (int)cta_rank) * 128 + row;      // global observation index
       // ---- stage this CTA's observations as the layer-0 A operand
       {
@@ -451,7 +465,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             }
           } else {
             const float* trg = p.target + (size_t)b * N + c0;
-            float* bc = sgn ? p.bc_minus : p.bc_plus;
+            float* bc = (tk.centre && !centre) ? nullptr : (sgn ? p.bc_minus : p.bc_plus);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const float4 t4 = __ldg(reinterpret_cast<const float4*>(trg + g * 4));
@@ -499,7 +513,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       if (etid == 0) {
         const float tot = (s_loss[0] + s_loss[1]) + (s_loss[2] + s_loss[3]);
         const int parts = p.chunks * CG;
-        const int cell = slot * 2 + sgn;
+        const bool folded = tk.centre && !centre;                 // centre task riding in a population launch
+        const int cell = folded ? p.pairs * 2 : slot * 2 + sgn;
         float* part = p.partial + (size_t)cell * parts;
         part[chunk * CG + (int)cta_rank] = tot;
         __threadfence();
@@ -509,7 +524,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           float s = 0.f;
           for (int c = 0; c < parts; ++c) s += __ldcg(part + c);
           const float r = -(s / ((float)p.B * (float)lay[L - 1].N));
-          if (sgn) p.ret_minus[j] = r; else p.ret_plus[j] = r;
+          if (folded) p.centre_out[0] = r;
+          else if (sgn) p.ret_minus[j] = r;
+          else p.ret_plus[j] = r;
           p.counters[cell] = 0u;
         }
       }
@@ -538,13 +555,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     auto setup = [&](int task, int l, int n0, int kb, StageDesc& d) {
       if (task != cached_task) {            // two dependent global loads: once per task, not per stage
         cached_task = task;
-        const int sgn = (task / p.chunks) % p.n_signs;
-        const int slot = task / (p.chunks * p.n_signs);
-        const int j = p.order ? p.order[slot] : slot;
-        const int64_t off_j = centre ? 0 : p.offsets[j];
-        cached_trow = centre ? p.theta : p.table + off_j;
-        cached_trow16 = centre ? p.theta16 : p.table16 + off_j;
-        cached_ssig = centre ? 0.f : (sgn ? -p.sigma : p.sigma);
+        const TaskId tk = decode_task(p, task, centre);
+        const int j = (!tk.centre && p.order) ? p.order[tk.slot] : tk.slot;
+        const int64_t off_j = tk.centre ? 0 : p.offsets[j];
+        cached_trow = tk.centre ? p.theta : p.table + off_j;
+        cached_trow16 = tk.centre ? p.theta16 : p.table16 + off_j;
+        cached_ssig = tk.centre ? 0.f : (tk.sgn ? -p.sigma : p.sigma);
       }
       const int K = lay[l].K;
       const int rows = min(256, lay[l].N - n0) / CG;          // this CTA's share of the B tile
@@ -735,7 +751,9 @@ int run_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream, const char* who)
   ESTK_CHECK_ARG(p.pairs >= 1 && p.pairs <= ESTK_MAX_POPULATION / 2, "%s: pairs=%d", who, p.pairs);
   p.chunks = p.B / (128 * cg);
   ESTK_CHECK_ARG(p.chunks * cg <= kEvalMaxChunks, "%s: batch too large", who);
-  p.n_tasks = p.pairs * p.n_signs * p.chunks;
+  p.n_centre = p.centre_out ? p.chunks : 0;
+  ESTK_CHECK_ARG(!p.centre_out || p.pairs * 2 < ESTK_MAX_POPULATION, "%s: population too large to fold the centre task", who);
+  p.n_tasks = p.n_centre + p.pairs * p.n_signs * p.chunks;
   { const char* e = getenv("ESTK_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.partial = ctx->eval_partial;
   p.counters = ctx->counters;
@@ -748,7 +766,8 @@ extern "C" int estk_eval_mlp_bf16(estk_ctx* ctx, const estk_mlp_desc* desc, cons
                                   const float* table, const int64_t* offsets, const int32_t* order,
                                   int32_t pairs, float sigma, const float* obs, const float* target,
                                   int32_t B, float* returns_plus, float* returns_minus, float* bc_plus,
-                                  float* bc_minus, int32_t bc_obs, int32_t bc_dim, void* stream) {
+                                  float* bc_minus, int32_t bc_obs, int32_t bc_dim, float* centre_return_out,
+                                  void* stream) {
   ESTK_CHECK_ARG(ctx && desc && theta && table && offsets && obs && target && returns_plus && returns_minus,
                  "estk_eval_mlp_bf16: null argument");
   ESTK_CHECK_ARG((bc_plus == nullptr) == (bc_minus == nullptr), "estk_eval_mlp_bf16: bc_plus/bc_minus must both be set or both null");
@@ -759,7 +778,7 @@ extern "C" int estk_eval_mlp_bf16(estk_ctx* ctx, const estk_mlp_desc* desc, cons
   p.pairs = pairs; p.sigma = sigma; p.obs = obs; p.target = target; p.B = B;
   p.ret_plus = returns_plus; p.ret_minus = returns_minus;
   p.bc_plus = bc_plus; p.bc_minus = bc_minus; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
-  p.n_signs = 2;
+  p.n_signs = 2; p.centre_out = centre_return_out;
   return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_bf16");
 }
 
@@ -804,7 +823,7 @@ extern "C" int estk_eval_mlp_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, con
                                    const int64_t* offsets, const int32_t* order, int32_t pairs, float sigma,
                                    const float* obs, const float* target, int32_t B, float* returns_plus,
                                    float* returns_minus, float* bc_plus, float* bc_minus, int32_t bc_obs,
-                                   int32_t bc_dim, void* stream) {
+                                   int32_t bc_dim, float* centre_return_out, void* stream) {
   ESTK_CHECK_ARG(ctx && desc && theta && theta16 && table && table16 && offsets && obs && target &&
                  returns_plus && returns_minus, "estk_eval_mlp_bf16s: null argument");
   ESTK_CHECK_ARG((bc_plus == nullptr) == (bc_minus == nullptr), "estk_eval_mlp_bf16s: bc_plus/bc_minus must both be set or both null");
@@ -817,7 +836,7 @@ extern "C" int estk_eval_mlp_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, con
   p.pairs = pairs; p.sigma = sigma; p.obs = obs; p.target = target; p.B = B;
   p.ret_plus = returns_plus; p.ret_minus = returns_minus;
   p.bc_plus = bc_plus; p.bc_minus = bc_minus; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
-  p.n_signs = 2;
+  p.n_signs = 2; p.centre_out = centre_return_out;
   return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_bf16s");
 }
 

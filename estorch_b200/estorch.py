@@ -269,6 +269,7 @@ class ES:
         self._active = self._slots[0] if self._slots else None
         self.step = 0
         self._generation = 0     # total generations ever run: indexes the noise offsets (never reset)
+        self._pending_centre = False
 
     # ------------------------------------------------------------------ setup helpers
     def _make_module(self):
@@ -540,9 +541,15 @@ class ES:
                              self.sigma, self._xref, self._obs, self._tgt, R[pb: pb + pl],
                              R[pairs + pb: pairs + pb + pl], self._conv_scratch)
         else:
+            kw = self._eval_kw(slot)
+            folded = self._pending_centre
+            if folded:        # the previous generation's post-update rollout rides in this launch
+                kw["centre_out"] = self._episode
             be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
-                        self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
-                        **self._eval_kw(slot))
+                        self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl], **kw)
+            if folded:        # theta is still the previous update's result here (estorch.py:182-185)
+                be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
+                self._pending_centre = False
         self._all_gather_halves(R)
         ad = self._adam_desc(slot.optimizer)
         if self.n_workers == 1:
@@ -553,13 +560,20 @@ class ES:
                          self.n_parameters, self._grad, self._ranks, None)
             self._all_reduce(self._grad)
             be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
+        self._best_slot = slot
+        # post-update rollout (estorch.py:181-185).  It is a single 100 us task, so when nobody
+        # can observe it before the next generation (no log() due, not the last generation) it
+        # is deferred and folded into the next generation's evaluate launch.
+        if (self._precision in ("bf16", "bf16s") and not self._is_conv and not self._stop
+                and (self.step + 1) % self._log_interval != 0 and self.step + 1 < self.n_steps):
+            self._pending_centre = True
+            return
         if self._is_conv:
             be.eval_conv_vbn(self._spec.n_actions, slot.theta, None, None, None, 1, 0.0, self._xref, self._obs,
                              self._tgt, self._episode, None, self._conv_scratch)
         else:
             be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, **self._eval_kw(slot, True))
         be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
-        self._best_slot = slot
 
     @property
     def population_parameters(self):

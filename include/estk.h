@@ -136,13 +136,16 @@ ESTK_API int estk_eval_mlp(estk_ctx* ctx, const estk_mlp_desc* desc, const float
  * every layer input width a multiple of 64 in [64,512], every output width a
  * multiple of 32 in [32,512], B a multiple of 256; otherwise
  * ESTK_ERR_UNSUPPORTED (estk_eval_mlp_bf16_supported() tells in advance).
- * Returns agree with the fp32 path to ~1e-2 relative (stated in the tests). */
+ * Returns agree with the fp32 path to ~1e-2 relative (stated in the tests).
+ * centre_return_out (nullable): additionally evaluate theta itself (sigma = 0) in
+ * the same launch and write its return there -- the estorch.py:182 rollout of the
+ * previous update folded into this generation's launch. */
 ESTK_API int estk_eval_mlp_bf16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
                        const float* table, const int64_t* offsets, const int32_t* order,
                        int32_t pairs, float sigma, const float* obs, const float* target, int32_t B,
                        float* returns_plus, float* returns_minus,
                        float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim,
-                       void* stream);
+                       float* centre_return_out, void* stream);
 ESTK_API int estk_eval_mlp_center_bf16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
                               const float* obs, const float* target, int32_t B,
                               float* return_out, float* bc_out, int32_t bc_obs, int32_t bc_dim,
@@ -162,7 +165,7 @@ ESTK_API int estk_eval_mlp_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, const
                         const float* obs, const float* target, int32_t B,
                         float* returns_plus, float* returns_minus,
                         float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim,
-                        void* stream);
+                        float* centre_return_out, void* stream);
 ESTK_API int estk_eval_mlp_center_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
                                const uint16_t* theta16, const float* obs, const float* target, int32_t B,
                                float* return_out, float* bc_out, int32_t bc_obs, int32_t bc_dim,

@@ -223,3 +223,33 @@ def test_conv_vbn_policy_fused_generation_vs_oracle():
     with torch.no_grad():
         out = es.policy(obs.to(es._dev))
     assert abs(float(-((out - tgt.to(es._dev)) ** 2).mean()) - rec["episode"]) < 1e-3 * abs(ep)
+
+
+def test_deferred_post_update_rollout_is_equivalent():
+    """With log_interval > 1 the post-update rollout of a generation is folded into the next
+    generation's evaluate launch; everything observable must be identical to log_interval = 1."""
+    dims = [128, 512, 288]
+    g = torch.Generator().manual_seed(2)
+    obs, tgt = torch.randn(256, 128, generator=g), torch.randn(256, 288, generator=g)
+    out = {}
+    for li in (1, 3):
+        seen = []
+
+        class Q(E.ES):
+            def log(self):
+                seen.append((self.step, self.episode_reward, self.best_reward))
+        torch.manual_seed(4)
+        es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=128, sigma=0.02, policy_kwargs={"dims": dims},
+               agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22,
+               log_interval=li)
+        assert es._precision == "bf16s"
+        es.train(n_steps=7)
+        out[li] = dict(theta=es._slots[0].theta.clone(), best=es._slots[0].best_theta.clone(), seen=seen,
+                       ep=es.episode_reward, br=es.best_reward, ret=es.population_returns.copy())
+    a, b = out[1], out[3]
+    assert torch.equal(a["theta"], b["theta"]) and torch.equal(a["best"], b["best"])
+    assert a["ep"] == b["ep"] and a["br"] == b["br"]
+    np.testing.assert_array_equal(a["ret"], b["ret"])
+    assert [s for s, _, _ in b["seen"]] == [2, 5] and len(a["seen"]) == 7
+    for step, ep, br in b["seen"]:                     # the logged generations report the same values
+        assert (step, ep, br) == a["seen"][step]
