@@ -202,6 +202,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 packed-bf16x2 words per lane back into TMEM (the activation stash, see the epilogue)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 ld_noise4u(const uint4* p) {
   uint4 v;
@@ -279,7 +288,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
   uint64_t* bar_empty = bars + kStages;      // [kStages]  (local)
   uint64_t* bar_acc = bars + 2 * kStages;    // layer accumulated (local)
   uint64_t* bar_h = bars + 2 * kStages + 1;  // activations in place (leader's is used)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  uint64_t* bar_acc0 = bars + 2 * kStages + 2;   // first N-tile of a two-tile layer accumulated (local)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 3);
   float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kNumEpiWarps]
   int* s_prog = reinterpret_cast<int*>(s_loss + kNumEpiWarps);   // n-groups started by the producers
 
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       mbar_init(smem_u32(bar_empty + s), 1);
     }
     mbar_init(smem_u32(bar_acc), 1);
+    mbar_init(smem_u32(bar_acc0), 1);
     mbar_init(smem_u32(bar_h), CG * kNumEpiWarps);
     fence_barrier_init();
   }
@@ -367,7 +378,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
                   }
                 }
                 umma_commit<CG>(smem_u32(bar_empty + stage));          // frees the ring slot (both CTAs)
-                if (n0 + 256 >= N && kb + nsub == K / kBlockK) umma_commit<CG>(smem_u32(bar_acc));
+                if (kb + nsub == K / kBlockK) {
+                  if (n0 + 256 >= N) umma_commit<CG>(smem_u32(bar_acc));     // layer accumulated
+                  else umma_commit<CG>(smem_u32(bar_acc0));                  // tile 0 of 2: its drain overlaps tile 1's MMAs
+                }
               }
               __syncwarp();
               PROF_ADD(3, ti0);
@@ -383,7 +397,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;             // observation row inside the CTA's 128
     const int etid = (warp - 2) * 32 + lane;   // 0..127
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, acc0_phase = 0;
     const bool eprof = prof && warp == 2;
     const long long te0 = eprof ? clock64() : 0ll;
     for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
@@ -416,95 +430,131 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       }
       if (eprof) atomicAdd(&g_tc_prof[11], (unsigned long long)(clock64() - to0));
       float loss = 0.f;
+      const uint32_t trow_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int l = 0; l < L; ++l) {
         const long long tb0 = eprof ? clock64() : 0ll;
         const int N = lay[l].N;
         float* bias = sBias + (l & 1) * kMaxW;
-        for (int o = etid; o < N; o += 32 * kNumEpiWarps)
-          bias[o] = fmaf(ssig, ld_noise1(trow + lay[l].bbase + o), __ldg(p.theta + lay[l].bbase + o));
-        named_bar_sync(1, 32 * kNumEpiWarps);   // publishes bias[] among the epilogue warps
-        if (l == 0) {
-          // the staged observations are this task's layer-0 input (the previous task's
-          // TMEM reads are long done): release the MMA warp
-          fence_proxy_async();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h), 0);   // layer 0: one hand-over for the whole input
-        }
-        if (eprof) atomicAdd(&g_tc_prof[12], (unsigned long long)(clock64() - tb0));
-        // ---- wait for the layer's accumulators
-        const long long ta0 = eprof ? clock64() : 0ll;
-        mbar_wait(smem_u32(bar_acc), acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (eprof) atomicAdd(&g_tc_prof[13], (unsigned long long)(clock64() - ta0));
-        const long long tx0 = eprof ? clock64() : 0ll;
-        const bool last = (l == L - 1);
-        // two 32-column TMEM loads in flight per wait
-        auto consume = [&](const uint32_t (&v)[32], int c0) {
-          float bv[32];
-          {
-            const uint32_t baddr = smem_u32(bias + c0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 t = ld_shared_v4(baddr + g * 16);
-              bv[g * 4 + 0] = t.x; bv[g * 4 + 1] = t.y; bv[g * 4 + 2] = t.z; bv[g * 4 + 3] = t.w;
-            }
-          }
-          if (!last) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              pk[e] = pack_bf16_relu(__uint_as_float(v[2 * e]) + bv[2 * e],
-                                     __uint_as_float(v[2 * e + 1]) + bv[2 * e + 1]);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {      // 4 chunks of 8 output features = 16 bytes of bf16
-              const int col = c0 + g * 8;
-              const uint32_t addr = smem_u32(sH + (col >> 6) * kKBlockBytes) + sw128_offset(row, (col & 63) >> 3);
-              st_shared_v4(addr, pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-            }
-          } else {
-            const float* trg = p.target + (size_t)b * N + c0;
-            float* bc = (tk.centre && !centre) ? nullptr : (sgn ? p.bc_minus : p.bc_plus);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(trg + g * 4));
-              const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int o = c0 + g * 4 + e;
-                const float y = __uint_as_float(v[g * 4 + e]) + bv[g * 4 + e];
-                const float d = y - tv[e];
-                loss = fmaf(d, d, loss);
-                if (bc) {
-                  const int64_t idx = (int64_t)b * N + o;
-                  if (b < p.bc_obs && idx < p.bc_dim) bc[(size_t)j * p.bc_dim + idx] = y;
-                }
-              }
-            }
-          }
-        };
-        const uint32_t trow_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        // this layer's output is the next layer's input: hand it over in halves so the
-        // next layer's MMAs on k-blocks 0..3 (which only overwrite TMEM columns < 256,
-        // already drained) overlap the second half of this epilogue
+        // this layer's output is the next layer's input: it is handed over in halves
+        // (k-blocks 0..3, then 4..7) so the next layer's first MMAs overlap the rest of
+        // this epilogue
         auto hand_over = [&]() {
           fence_proxy_async();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h), 0);
         };
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          if (!last && c0 == 256) hand_over();
+        // the staged observations are this task's layer-0 input (the previous task's TMEM
+        // reads are long done): release the MMA warp before anything else
+        if (l == 0) hand_over();
+        for (int o = etid; o < N; o += 32 * kNumEpiWarps)
+          bias[o] = fmaf(ssig, ld_noise1(trow + lay[l].bbase + o), __ldg(p.theta + lay[l].bbase + o));
+        named_bar_sync(1, 32 * kNumEpiWarps);   // publishes bias[] among the epilogue warps
+        if (eprof) atomicAdd(&g_tc_prof[12], (unsigned long long)(clock64() - tb0));
+        const bool last = (l == L - 1);
+        const bool two = N > 256;               // two N tiles: columns [0,256) and [256,N)
+        // bias + ReLU + round to bf16: 32 accumulator columns -> 16 packed words
+        auto pack = [&](const uint32_t (&v)[32], int c0, uint32_t (&pk)[16]) {
+          const uint32_t baddr = smem_u32(bias + c0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = ld_shared_v4(baddr + g * 16);
+            pk[g * 2 + 0] = pack_bf16_relu(__uint_as_float(v[g * 4 + 0]) + t.x, __uint_as_float(v[g * 4 + 1]) + t.y);
+            pk[g * 2 + 1] = pack_bf16_relu(__uint_as_float(v[g * 4 + 2]) + t.z, __uint_as_float(v[g * 4 + 3]) + t.w);
+          }
+        };
+        // W packed words (2*W output features starting at feature f0) -> activations in smem
+        auto store_h = [&](const uint32_t* pk, int f0, int words) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {          // chunks of 8 output features = 16 bytes of bf16
+            if (g * 4 < words) {
+              const int col = f0 + g * 8;
+              const uint32_t addr = smem_u32(sH + (col >> 6) * kKBlockBytes) + sw128_offset(row, (col & 63) >> 3);
+              st_shared_v4(addr, pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+            }
+          }
+        };
+        // last layer: fused squared error (and the behaviour characterisation)
+        auto loss_chunk = [&](const uint32_t (&v)[32], int c0) {
+          const uint32_t baddr = smem_u32(bias + c0);
+          const float* trg = p.target + (size_t)b * N + c0;
+          float* bc = (tk.centre && !centre) ? nullptr : (sgn ? p.bc_minus : p.bc_plus);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(trg + g * 4));
+            const float4 b4 = ld_shared_v4(baddr + g * 16);
+            const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int o = c0 + g * 4 + e;
+              const float y = __uint_as_float(v[g * 4 + e]) + bv[e];
+              const float d = y - tv[e];
+              loss = fmaf(d, d, loss);
+              if (bc) {
+                const int64_t idx = (int64_t)b * N + o;
+                if (b < p.bc_obs && idx < p.bc_dim) bc[(size_t)j * p.bc_dim + idx] = y;
+              }
+            }
+          }
+        };
+        if (two) {
+          // ---- tile 0 is accumulated while tile 1's MMAs still run (they read the
+          // activations in smem, so those cannot be overwritten yet): drain tile 0 now.
+          // Hidden layers park the result as packed bf16 pairs in TMEM columns the drain
+          // has already freed (columns [c0,c0+32) -> [c0/2,c0/2+16), in place).
+          const long long ta0 = eprof ? clock64() : 0ll;
+          mbar_wait(smem_u32(bar_acc0), acc0_phase);
+          acc0_phase ^= 1;
+          tc_fence_after();
+          if (eprof) atomicAdd(&g_tc_prof[13], (unsigned long long)(clock64() - ta0));
+          const long long tx0 = eprof ? clock64() : 0ll;
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t va[32];
+            tmem_ld32(trow_addr + (uint32_t)c0, va);
+            tmem_ld_wait();
+            if (last) {
+              loss_chunk(va, c0);
+            } else {
+              uint32_t pk[16];
+              pack(va, c0, pk);
+              tmem_st16(trow_addr + (uint32_t)(c0 >> 1), pk);
+            }
+          }
+          if (!last) tmem_st_wait();
+          if (eprof) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - tx0));
+        }
+        // ---- wait for the whole layer: every MMA that reads the activations has completed
+        const long long ta1 = eprof ? clock64() : 0ll;
+        mbar_wait(smem_u32(bar_acc), acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (eprof) atomicAdd(&g_tc_prof[13], (unsigned long long)(clock64() - ta1));
+        const long long tx1 = eprof ? clock64() : 0ll;
+        if (!last && two) {
+          // parked half -> activation k-blocks 0..3, first hand-over
+          for (int s0 = 0; s0 < 128; s0 += 32) {
+            uint32_t pk[32];
+            tmem_ld32(trow_addr + (uint32_t)s0, pk);
+            tmem_ld_wait();
+            store_h(pk, 2 * s0, 32);
+          }
+          hand_over();
+        }
+        for (int c0 = two ? 256 : 0; c0 < N; c0 += 32) {
           uint32_t va[32];
-          const long long tl0 = eprof ? clock64() : 0ll;
           tmem_ld32(trow_addr + (uint32_t)c0, va);
           tmem_ld_wait();
-          if (eprof) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - tl0));
-          consume(va, c0);
+          if (last) {
+            loss_chunk(va, c0);
+          } else {
+            uint32_t pk[16];
+            pack(va, c0, pk);
+            store_h(pk, c0, 16);
+          }
         }
         if (!last) hand_over();                  // second half (or the only one when N <= 256)
-        if (eprof) atomicAdd(&g_tc_prof[14], (unsigned long long)(clock64() - tx0));
+        if (eprof) atomicAdd(&g_tc_prof[14], (unsigned long long)(clock64() - tx1));
       }
       // ---- squared-error partial of this CTA; the last arriver combines them in fixed order
       loss = warp_sum_f(loss);
@@ -704,7 +754,7 @@ size_t tc_smem_bytes() {
   const int stages = 4 / kSubPerStage;
   const int stage_b = (CG == 2) ? kStageBytes : 2 * kStageBytes;
   return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)stages * stage_b + 2 * kMaxW * sizeof(float) +
-         (2 * stages + 2) * sizeof(uint64_t) + 128;
+         (2 * stages + 3) * sizeof(uint64_t) + 128;
 }
 
 template <int CG, bool S16>
