@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libestk.so")
+# ESTK_LIBRARY selects another build of the same library (A/B timing of kernel variants only)
+LIB_PATH = os.environ.get("ESTK_LIBRARY") or os.path.join(_HERE, "lib", "libestk.so")
 
 ESTK_MAX_LAYERS = 8
 ESTK_MAX_POPULATION = 32768

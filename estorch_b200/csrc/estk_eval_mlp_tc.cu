@@ -31,8 +31,10 @@
 // Roofline: 2*n*B*2*pairs flops per launch on the tensor pipe; the noise stream
 // 4*n*pairs bytes is read once from HBM (second sign from L2).
 #include "estk_common.cuh"
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
 
 __device__ unsigned long long g_tc_prof[32];   // ESTK_TC_DEBUG bit 8: per-role cycle counters of cluster 0 / CTA 0
 
@@ -44,8 +46,15 @@ constexpr int kKBlockBytes = 128 * kBlockK * 2;   // one [128 x 64] bf16 tile = 
 constexpr int kSubPerStage = 1;                   // k-blocks per ring stage (2 was measured: no gain, less ring depth)
 constexpr int kStageBytes = kSubPerStage * kKBlockBytes;   // B ring stage: [<=128 rows x 64] per k-block at CG=2
 constexpr int kNumEpiWarps = 4, kNumProdWarps = 8;
-constexpr int kProdGroups = 2, kProdGroupWarps = kNumProdWarps / kProdGroups;   // groups work on different ring stages concurrently
-constexpr int kThreadsTC = 32 * (2 + kNumEpiWarps + kNumProdWarps);   // 320
+// the producer warps form groups that work on different ring stages concurrently:
+// fp32 sources: 2 groups of 4 warps (theta and noise both through registers);
+// bf16 shadows: 4 groups of 2 warps (theta tile by TMA, only the noise through registers)
+__host__ __device__ constexpr int prod_groups(bool s16) { return s16 ? 4 : 2; }
+constexpr int kThreadsTC = 32 * (2 + kNumEpiWarps + kNumProdWarps);   // 448
+
+// TMA descriptors of the bf16 theta shadow, one per (layer, N tile): [N x K] row-major,
+// box [rows of the tile per CTA x 64], SWIZZLE_128B == the UMMA B-operand layout
+struct TcMaps { CUtensorMap m[ESTK_MAX_LAYERS][2]; };
 
 struct EvalTCParams {
   estk_mlp_desc desc;
@@ -128,6 +137,15 @@ __device__ __forceinline__ void mbar_arrive_on(uint32_t bar, uint32_t cta) {
         "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
         "}" ::"r"(bar), "r"(cta) : "memory");
   }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load into this CTA's shared memory, completion on this CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 // generic-proxy st.shared -> visible to the async proxy (tensor core reads of smem)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -247,6 +265,11 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ uint4 ld_shared_v4u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -274,9 +297,13 @@ __device__ __forceinline__ TaskId decode_task(const EvalTCParams& p, int task, b
 #define PROF_T() (PROF_ON ? clock64() : 0ll)
 #define PROF_ADD(i, t0) do { if (PROF_ON) atomicAdd(&g_tc_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
 
-template <int CG, bool S16>
-__global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTCParams p) {
-  constexpr int kStages = 4 / kSubPerStage;
+// 448 threads at 128 registers: the register file is allocated per 4 warps, so a 14-warp
+// block is charged as 16 warps and 144 registers per thread do not launch (measured)
+template <int CG, bool S16, int RING>
+__global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTCParams p,
+                                                                     const __grid_constant__ TcMaps maps) {
+  constexpr int kStages = RING;
+  constexpr int kProdGroups = prod_groups(S16), kProdGroupWarps = kNumProdWarps / kProdGroups;
   constexpr int kStageB = (CG == 2) ? kStageBytes : 2 * kStageBytes;   // up to 256 rows at CG=1
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -289,7 +316,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
   uint64_t* bar_acc = bars + 2 * kStages;    // layer accumulated (local)
   uint64_t* bar_h = bars + 2 * kStages + 1;  // activations in place (leader's is used)
   uint64_t* bar_acc0 = bars + 2 * kStages + 2;   // first N-tile of a two-tile layer accumulated (local)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 3);
+  uint64_t* bar_tma = bars + 2 * kStages + 3;    // [kStages] theta tile landed in the ring slot (local, bf16s only)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 3);
   float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kNumEpiWarps]
   int* s_prog = reinterpret_cast<int*>(s_loss + kNumEpiWarps);   // n-groups started by the producers
 
@@ -303,6 +331,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(bar_full + s), CG * kProdGroupWarps);
       mbar_init(smem_u32(bar_empty + s), 1);
+      mbar_init(smem_u32(bar_tma + s), 1);
     }
     mbar_init(smem_u32(bar_acc), 1);
     mbar_init(smem_u32(bar_acc0), 1);
@@ -391,6 +420,39 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
         }
       }
       PROF_ADD(0, tm0);
+    }
+  } else if (warp == 1) {
+    // =================================================================== theta-tile TMA (bf16 shadow sources)
+    // One thread walks the same (task, layer, n-tile, k-block) stage sequence as the
+    // producers and, as soon as a ring slot is free, has the TMA engine drop this CTA's
+    // [rows x 64] tile of the bf16 theta shadow into it -- already in the swizzled
+    // B-operand layout.  The producers then only stream the noise through registers and
+    // turn the slot into theta + s*sigma*eps in place.
+    if constexpr (S16) {
+      if (lane == 0) {
+        uint32_t cnt = 0;
+        for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
+          for (int l = 0; l < L; ++l) {
+            const int K = lay[l].K, N = lay[l].N;
+            for (int n0 = 0; n0 < N; n0 += 256) {
+              const int rows = min(256, N - n0) / CG;
+              const CUtensorMap* map = &maps.m[l][n0 ? 1 : 0];
+              for (int kb = 0; kb < K / kBlockK; ++kb, ++cnt) {
+                const uint32_t stage = cnt % kStages, ring_phase = (cnt / kStages) & 1u;
+                mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
+                if (!(p.dbg & 2)) {
+                  mbar_arrive_expect_tx(smem_u32(bar_tma + stage), (uint32_t)rows * 128u);
+                  tma_load_2d(smem_u32(sB + stage * kStageB), map, kb * kBlockK, n0 + (int)cta_rank * rows,
+                              smem_u32(bar_tma + stage));
+                } else {
+                  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_tma + stage)) : "memory");
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
     }
   } else if (warp >= 2 && warp < 2 + kNumEpiWarps) {
     // =================================================================== epilogue warps
@@ -585,16 +647,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     if (eprof) atomicAdd(&g_tc_prof[10], (unsigned long long)(clock64() - te0));
   } else if (warp >= 2 + kNumEpiWarps) {
     // =================================================================== weight producers
-    // Software-pipelined over the flattened (task, layer, n-group, k-block) stage
-    // sequence: while stage s is formed / stored / fenced, the 128-bit loads of
-    // stage s+1 are already in flight (item slot u is refilled as soon as it has
-    // been consumed), so L2/HBM latency overlaps the per-stage overhead.
-    // The producer warps form kProdGroups groups; group g builds stages g, g+G, g+2G, ...
-    // of the flattened sequence, so up to G stages' loads are in flight per SM and
-    // the groups' load / form / fence phases interleave.
+    // The producer warps form kProdGroups groups; group g builds stages g, g+G, g+2G, ... of
+    // the flattened (task, layer, n-tile, k-block) stage sequence, so G stages' loads are in
+    // flight per SM and the groups' load / form / fence phases interleave.
     const int pwarp = warp - 2 - kNumEpiWarps;
     const int pgroup = pwarp / kProdGroupWarps;
-    const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // 0..127 inside the group
+    const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // thread index inside the group
     constexpr int kPT = 32 * kProdGroupWarps;
     struct StageDesc { const float* th; const float* ep; const uint16_t* th16; const uint16_t* ep16; int K; int n_items; int sub_items; float ssig; };
     constexpr bool src16 = S16;
@@ -652,46 +710,41 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       const uint32_t sbase = smem_u32(sB + stage * kStageB);
       bool waited = false;
       if constexpr (src16) {
-        // bf16 shadow sources: one 128-bit load brings 8 elements, so a batch of 8
-        // items per thread (16 loads in flight) covers a whole [128 x 64] stage
-        for (int it0 = 0; it0 < cur.n_items; it0 += 8 * kPT) {
-          uint4 t16[8], e16[8];
+        // bf16 shadow sources.  The theta tile arrives by TMA (see warp 1); a group of 64
+        // threads streams the noise: 16 items (128-bit loads, 8 elements each) per thread
+        // cover the whole [128 x 64] stage, issued before the slot is even free.
+        // item u of a thread = tile row u*8 + r0, 16-byte chunk c0 of the 128-byte row
+        static_assert(kSubPerStage == 1 && kPT == 64, "bf16s producer: 64-thread groups, one k-block per stage");
+        const int r0 = ptid >> 3, c0 = ptid & 7;
+        const int rows = cur.sub_items >> 3;
+        const uint16_t* eptr = cur.ep16 + (size_t)r0 * cur.K + c0 * 8;
+        uint4 e16[16];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int it = it0 + u * kPT + ptid;
-            if (it < cur.n_items && !(p.dbg & 1)) {
-              const int sub = (kSubPerStage > 1) ? (it >= cur.sub_items) : 0, iq = it - sub * cur.sub_items;
-              const int64_t off = (int64_t)(iq >> 3) * cur.K + sub * kBlockK + (iq & 7) * 8;
-              t16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.th16 + off));
-              e16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.ep16 + off));
-            }
-          }
-          if (!waited) {
-            const long long tw0 = pprof ? clock64() : 0ll;
-            mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
-            waited = true;
-            if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
-          }
-          const long long tc0 = pprof ? clock64() : 0ll;
+        for (int u = 0; u < 16; ++u)
+          if (u * 8 + r0 < rows && !(p.dbg & 1))
+            e16[u] = ld_noise4u(reinterpret_cast<const uint4*>(eptr + (size_t)(u * 8) * cur.K));
+        const long long tw0 = pprof ? clock64() : 0ll;
+        mbar_wait(smem_u32(bar_tma + stage), ring_phase);          // theta tile landed (so the slot was free)
+        if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
+        const long long tc0 = pprof ? clock64() : 0ll;
+        // W = theta16 + (s*sigma)_bf16 * eps16, one packed fma per two elements, in place
+        // (exact product-sum, one rounding to bf16; sigma itself is rounded to bf16)
+        const uint32_t sg2 = pack_bf16(cur.ssig, cur.ssig);
+        const uint32_t taddr = sbase + (uint32_t)(r0 * 128 + ((c0 ^ r0) << 4));   // sw128_offset(u*8 + r0, c0) - u*1024
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int it = it0 + u * kPT + ptid;
-            if (it < cur.n_items) {
-              // W = theta16 + (s*sigma)_bf16 * eps16, one packed fma per two elements
-              // (exact product-sum, one rounding to bf16; sigma itself is rounded to bf16)
-              const uint32_t sg2 = pack_bf16(cur.ssig, cur.ssig);
-              const uint32_t tw[4] = {t16[u].x, t16[u].y, t16[u].z, t16[u].w};
-              const uint32_t ew[4] = {e16[u].x, e16[u].y, e16[u].z, e16[u].w};
-              uint32_t w[4];
+        for (int u = 0; u < 16; ++u) {
+          if (u * 8 + r0 < rows) {
+            const uint4 t = ld_shared_v4u(taddr + u * 1024);
+            const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+            const uint32_t ew[4] = {e16[u].x, e16[u].y, e16[u].z, e16[u].w};
+            uint32_t w[4];
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(w[c]) : "r"(sg2), "r"(ew[c]), "r"(tw[c]));
-              const int sub = (kSubPerStage > 1) ? (it >= cur.sub_items) : 0, iq = it - sub * cur.sub_items;
-              st_shared_v4(sbase + sub * kKBlockBytes + sw128_offset(iq >> 3, iq & 7), w[0], w[1], w[2], w[3]);
-            }
+            for (int c = 0; c < 4; ++c)
+              asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(w[c]) : "r"(sg2), "r"(ew[c]), "r"(tw[c]));
+            st_shared_v4(taddr + u * 1024, w[0], w[1], w[2], w[3]);
           }
-          if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
         }
+        if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
       } else {
       for (int it0 = 0; it0 < cur.n_items; it0 += 4 * kPT) {
           // every 128-bit load of the batch is issued up front (16 in flight per thread) ...
@@ -750,17 +803,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
 }
 
 template <int CG>
-size_t tc_smem_bytes() {
-  const int stages = 4 / kSubPerStage;
+size_t tc_smem_bytes(int stages) {
   const int stage_b = (CG == 2) ? kStageBytes : 2 * kStageBytes;
   return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)stages * stage_b + 2 * kMaxW * sizeof(float) +
-         (2 * stages + 3) * sizeof(uint64_t) + 128;
+         (3 * stages + 3) * sizeof(uint64_t) + 128;
 }
 
-template <int CG, bool S16>
-int launch_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream) {
-  const size_t smem = tc_smem_bytes<CG>();
-  ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_tc_kernel<CG, S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int CG, bool S16, int RING>
+int launch_tc(estk_ctx* ctx, EvalTCParams& p, const TcMaps* maps, cudaStream_t stream) {
+  const size_t smem = tc_smem_bytes<CG>(RING);
+  ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_tc_kernel<CG, S16, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int clusters = ctx->sm_count / CG;
   if (clusters > p.n_tasks) clusters = p.n_tasks;
   cudaLaunchConfig_t cfg = {};
@@ -775,7 +827,58 @@ int launch_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_tc_kernel<CG, S16>, p));
+  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_tc_kernel<CG, S16, RING>, p, *maps));
+  return ESTK_OK;
+}
+
+// ---- TMA descriptors of the theta shadow (host side)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int build_theta_maps(const estk_mlp_desc& d, const uint16_t* theta16, int cg, TcMaps* out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ESTK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      estk_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return ESTK_ERR_CUDA;
+    }
+    encode = (EncodeTiledFn)fn;
+  }
+  // single-entry cache: the descriptors only depend on the shadow's address and the layer shapes
+  static thread_local struct { const uint16_t* ptr; estk_mlp_desc desc; int device; bool valid; TcMaps maps; } cache = {};
+  int dev = -1;
+  ESTK_CUDA(cudaGetDevice(&dev));
+  if (cache.valid && cache.ptr == theta16 && cache.device == dev && memcmp(&cache.desc, &d, sizeof(d)) == 0) {
+    *out = cache.maps;
+    return ESTK_OK;
+  }
+  memset(out, 0, sizeof(*out));
+  int64_t pb = 0;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const int K = d.dims[l], N = d.dims[l + 1];
+    for (int t = 0; t < 2; ++t) {
+      const int n0 = t * 256;
+      const int Nt = (n0 < N) ? (N - n0 < 256 ? N - n0 : 256) : (N < 256 ? N : 256);   // tile 1 of a one-tile layer: unused copy
+      const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+      const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+      const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(Nt / cg)};
+      const cuuint32_t estride[2] = {1, 1};
+      const CUresult r = encode(&out->m[l][t], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(theta16 + pb), gdim, gstride,
+                                box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        estk_set_error("cuTensorMapEncodeTiled failed (%d) for layer %d tile %d [N=%d K=%d box %dx%d]", (int)r, l, t, N, K,
+                       Nt / cg, kBlockK);
+        return ESTK_ERR_CUDA;
+      }
+    }
+    pb += (int64_t)K * N + N;
+  }
+  cache.ptr = theta16; cache.desc = d; cache.device = dev; cache.maps = *out; cache.valid = true;
   return ESTK_OK;
 }
 
@@ -807,7 +910,16 @@ int run_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream, const char* who)
   { const char* e = getenv("ESTK_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.partial = ctx->eval_partial;
   p.counters = ctx->counters;
-  return p.theta16 ? launch_tc<2, true>(ctx, p, stream) : launch_tc<2, false>(ctx, p, stream);
+  // B ring depth: bf16s runs 4 producer groups and wants the 5 stages that fit beside the
+  // 128 KB of activations (ESTK_TC_RING=4|5 overrides; perf triage only)
+  static const int ring_env = [] { const char* e = getenv("ESTK_TC_RING"); return e ? atoi(e) : 0; }();
+  static thread_local TcMaps maps;
+  if (p.theta16) {
+    const int rc = build_theta_maps(p.desc, p.theta16, cg, &maps);
+    if (rc != ESTK_OK) return rc;
+    return ring_env == 4 ? launch_tc<2, true, 4>(ctx, p, &maps, stream) : launch_tc<2, true, 5>(ctx, p, &maps, stream);
+  }
+  return ring_env == 5 ? launch_tc<2, false, 5>(ctx, p, &maps, stream) : launch_tc<2, false, 4>(ctx, p, &maps, stream);
 }
 
 }  // namespace
