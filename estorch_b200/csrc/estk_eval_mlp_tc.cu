@@ -10,26 +10,38 @@
 // UMMA M = 256).  Per layer  D[obs, out] = H[obs, in] * W_s[out, in]^T :
 //   A operand  activations H, 128 observation rows per CTA, bf16, K-major,
 //              128B-swizzled, RESIDENT in shared memory across layers (in place);
-//   B operand  W_s = theta + s*sigma*eps, formed ON THE FLY by the producer
-//              warps (128-bit loads of theta (L2) and of the pair's noise row,
-//              one FMA, cvt.rn.bf16x2, 16-byte swizzled st.shared) into a ring
-//              of [N/CG x 64] tiles -- the perturbed weights never exist in
-//              global memory; each CTA of the pair forms its half of N;
+//   B operand  W_s = theta + s*sigma*eps, formed ON THE FLY into a ring of
+//              [N/CG x 64] tiles -- the perturbed weights never exist in global
+//              memory; each CTA of the pair forms its half of N.
+//              bf16 shadow sources ("bf16s"): the TMA engine drops the theta tile
+//              into the free ring slot already in the swizzled operand layout
+//              (cuTensorMapEncodeTiled, SWIZZLE_128B); a producer group streams the
+//              pair's noise row with 128-bit loads and turns the slot into
+//              theta + s*sigma*eps in place (ld.shared, fma.rn.bf16x2, st.shared).
+//              fp32 sources ("bf16"): theta and noise both through registers,
+//              one FMA, cvt.rn.bf16x2, 16-byte swizzled st.shared;
 //   D          the WHOLE layer output [128 x <=512] fp32 lives in TMEM (512
-//              columns); the epilogue warps read it back (tcgen05.ld), add the
-//              perturbed bias, apply ReLU, round to bf16 and overwrite H; the
-//              last layer is fused with the squared-error reduction instead.
-// Warp roles per CTA: w0 MMA issuer (leader CTA only), w1 TMEM allocator (an L2
-// bulk-prefetch role for w1 was tried and removed: it raised DRAM traffic 5x by
-// evicting rows the offset-sorted order would have re-used, with no speed-up),
-// w2-5 epilogue (TMEM lane quarter = warp % 4), w6-13 weight producers (2 groups of 4).
-// Pipelines: full/empty mbarriers on the B ring, acc_full (layer accumulated),
-// h_ready (next layer's activations in place).  Persistent: clusters loop over
-// tasks; the two signs of a pair run on neighbouring clusters at the same time,
-// so the second read of the noise row is an L2 hit.
+//              columns) as two N tiles.  Tile 0 is drained while tile 1's MMAs
+//              still run: bias, ReLU, bf16, parked as packed pairs in the TMEM
+//              columns its own drain has freed (the activations in smem are still
+//              being read).  When the layer is accumulated the parked half moves
+//              to smem (k-blocks 0..3, first hand-over), then tile 1 is drained
+//              straight into k-blocks 4..7 (second hand-over) under the next
+//              layer's first MMAs.  The last layer is fused with the squared-error
+//              reduction instead.
+// Warp roles per CTA: w0 MMA issuer (leader CTA only), w1 TMEM allocator + theta-tile
+// TMA thread, w2-5 epilogue (TMEM lane quarter = warp % 4), w6-13 weight producers
+// (bf16s: 4 groups of 2 warps; fp32 sources: 2 groups of 4).
+// Pipelines: full/empty (+ tma) mbarriers on the B ring, acc0 / acc (first tile / layer
+// accumulated), h_ready (next layer's activations in place).  Persistent: clusters
+// loop over tasks; the two signs of a pair run on neighbouring clusters at the same
+// time, so the second read of the noise row is an L2 hit.
 //
 // Roofline: 2*n*B*2*pairs flops per launch on the tensor pipe; the noise stream
-// 4*n*pairs bytes is read once from HBM (second sign from L2).
+// 4*n*pairs bytes (2*n*pairs from the bf16 shadow) is read once from HBM (second sign
+// from L2).  Measured and rejected (profiles/README.md): L2 bulk-prefetch warp, 2-k-block
+// ring stages, register-pipelined producer refill, 8 epilogue + 6 producer warps,
+// 16-column double-buffered TMEM drains, bias fetched a layer ahead / by a 15th warp.
 #include "estk_common.cuh"
 #include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
@@ -98,21 +110,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-// wait with CLUSTER-scope acquire: only for barriers that receive arrivals from the
-// peer CTA (full[], h_ready on the leader).  ptxas pairs a cluster-scope acquire
-// with CCTL.IVALL (L1 invalidate + drain of outstanding loads), so the producers
-// and the epilogue use the CTA-scope variant below on their local barriers.
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
+// mbarrier waits use the CTA-scope form: ptxas pairs a cluster-scope acquire with
+// CCTL.IVALL (L1 invalidate + drain of outstanding loads)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -149,9 +148,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 // generic-proxy st.shared -> visible to the async proxy (tensor core reads of smem)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
