@@ -149,7 +149,7 @@ def run_reference_arm(args, wl, rank, world):
             "config": workload_config(args, wl, world), "cpu_baseline": cb,
             "e2e": {"value": r["value"], "unit": "generations/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, wl, world):
@@ -285,12 +285,16 @@ def run_ours(args, wl, rank, world, local_rank):
               "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": flops_eval / t_eval / 1e9 / peaks["tensor"],
               "ms": t_eval, "traffic": None, "algorithmic_bytes": bytes_eval, "flops": flops_eval,
               "hbm_frac_of_noise_stream": bytes_eval / t_eval / 1e6 / peaks["hbm"]}
-    # DRAM traffic per launch from the committed `ncu --set full` capture of exactly these
-    # kernels / shapes on one GPU (profiles/r01_ncu_full_summary.txt); null elsewhere
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    # `ncu --set full` capture of exactly these kernels / shapes on one GPU
+    # (profiles/ncu_traffic.json <- profiles/r01s2_ncu_full_summary.txt); null elsewhere
     if args.workload == "north_star" and world == 1:
-        k_grad["traffic"] = 1.084050e9 + 5.2e6
-        if es._precision == "bf16s":
-            k_eval["traffic"] = 0.557642e9 + 3.4e6
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            k_grad["traffic"] = tr.get(k_grad["kernel"])
+            k_eval["traffic"] = tr.get(k_eval["kernel"])
+        except (OSError, ValueError):
+            pass
     dominant = k_eval if t_eval >= t_grad else k_grad
     roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = dominant["kernel"]
@@ -316,7 +320,19 @@ def run_ours(args, wl, rank, world, local_rank):
                     "d2h_bytes_per_step": int(4 * P + 32)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": [k_grad, k_eval],
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -334,6 +350,12 @@ def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     wl = WORKLOADS[args.workload]
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version
+    # banner at communicator creation, ...) is sent to stderr instead
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args, wl, rank, world)
         return

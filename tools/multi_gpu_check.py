@@ -20,7 +20,8 @@ for name, cls, dims, kw, akw in (("ES", E.ES, [128, 512, 288], {}, {}),
         def log(self):
             pass
     es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=256, sigma=0.02, policy_kwargs={"dims": dims},
-           agent_kwargs=dict(obs=obs, target=tgt, **akw), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22, **kw)
+           agent_kwargs=dict(obs=obs, target=tgt, **akw), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22,
+           log_interval=int(os.environ.get("LOG_INTERVAL", "1")), **kw)   # > 1: the post-update rollout is folded
     assert es._fused and es.n_workers == world
     es.train(n_steps=3)
     theta = torch.stack([s.theta for s in es._slots])
