@@ -314,7 +314,19 @@ class ES:
         print(f'Max Reward: {self.best_reward}')
 
     # -- lazily synchronised attributes (documented at estorch.py:108-117) --
+    def _flush_pending_centre(self):
+        """A deferred post-update rollout (see _fused_generation) is run now: something
+        wants to observe episode_reward / the best snapshot before the next generation."""
+        if getattr(self, "_pending_centre", False):
+            slot = self._active
+            self._be.eval_mlp_center(self._spec.dims, slot.theta, self._obs, self._tgt, self._episode,
+                                     **self._eval_kw(slot, True))
+            self._be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
+            self._pending_centre = False
+            self._host_cache = {}
+
     def _slot_state(self):
+        self._flush_pending_centre()
         key = ("state", id(self._active), self.step, self._gen_token)
         if self._host_cache.get("key") != key:
             self._host_cache = {"key": key, "state": read_state(self._active.state)}
@@ -348,6 +360,7 @@ class ES:
     def best_policy_dict(self):
         if "_best_policy_dict" in self.__dict__:
             return self.__dict__["_best_policy_dict"]
+        self._flush_pending_centre()
         slot = self._best_slot if getattr(self, "_best_slot", None) is not None else self._active
         if slot is None or self.best_reward == -float("inf"):
             raise AttributeError("best_policy_dict is set after the first improving generation")
@@ -706,6 +719,7 @@ class ES:
         step counters / best snapshot per (policy, optimizer) slot, the generation
         counter and noise seed (the table is regenerated from the seed), and the host
         scalars of the algorithm."""
+        self._flush_pending_centre()
         self._host_cache = {}
         slots = []
         for s_ in self._slots:

@@ -17,9 +17,31 @@ def _np(t):
 class OracleBackend:
     name = "oracle"
 
-    def __init__(self):
+    def __init__(self, tensor_core=False):
+        """``tensor_core=True`` also emulates the tcgen05 evaluate modes ("bf16" / "bf16s",
+        with the oracle's bf16 rounding model) so that the host logic around them -- shadows,
+        the folded post-update rollout -- runs on CPU."""
         self.device = torch.device("cpu")
         self.sm_count, self.cc, self.launches = 0, (0, 0), 0
+        self.tensor_core = tensor_core
+        self.centre_folds = 0      # evaluate launches that carried a folded centre task
+
+    def eval_supports_bf16(self, dims, B):
+        ok = all(k % 64 == 0 and 64 <= k <= 512 for k in dims[:-1]) and \
+            all(n % 32 == 0 and 32 <= n <= 512 for n in dims[1:]) and B % 256 == 0
+        return bool(self.tensor_core and ok)
+
+    def shadow_bf16(self, src, dst):
+        dst.copy_(torch.from_numpy(orc.round_bf16(_np(src))).to(torch.bfloat16))
+
+    @staticmethod
+    def _exact_biases(rows, exact, dims):
+        idx = 0
+        for i in range(len(dims) - 1):
+            idx += dims[i] * dims[i + 1]
+            rows[..., idx: idx + dims[i + 1]] = exact[..., idx: idx + dims[i + 1]]
+            idx += dims[i + 1]
+        return rows
 
     def alloc(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype)
@@ -51,8 +73,21 @@ class OracleBackend:
             eps_out.copy_(torch.from_numpy(eps[sl]))
 
     def eval_mlp(self, dims, theta, table, offsets, order, pairs, sigma, obs, target, ret_plus, ret_minus,
-                 bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32", **_):
+                 bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32", centre_out=None, **_):
         pop, _ = orc.sample_population(_np(theta), _np(table), _np(offsets), sigma)
+        if precision in ("bf16", "bf16s"):
+            assert self.tensor_core and bc_plus is None
+            rows = pop.copy() if precision == "bf16" else self._exact_biases(
+                orc.sample_population_bf16s(_np(theta), _np(table), _np(offsets), sigma), pop, list(dims))
+            rets = np.array([orc.synthetic_return(orc.mlp_forward_bf16(r, list(dims), _np(obs)), _np(target))
+                             for r in rows], dtype=np.float32)
+            ret_plus.copy_(torch.from_numpy(rets[:pairs]))
+            ret_minus.copy_(torch.from_numpy(rets[pairs:]))
+            if centre_out is not None:       # the folded post-update rollout of the previous generation
+                self.centre_folds += 1
+                self.eval_mlp_center(dims, theta, obs, target, centre_out, precision=precision)
+            return
+        assert centre_out is None
         rets, bcs = orc.evaluate_population(pop, list(dims), _np(obs), _np(target), bc_obs, bc_dim)
         ret_plus.copy_(torch.from_numpy(rets[:pairs]))
         ret_minus.copy_(torch.from_numpy(rets[pairs:]))
@@ -61,7 +96,12 @@ class OracleBackend:
             bc_minus.copy_(torch.from_numpy(bcs[pairs:]))
 
     def eval_mlp_center(self, dims, theta, obs, target, ret_out, bc_out=None, bc_obs=0, bc_dim=0, precision="fp32", **_):
-        out = orc.mlp_forward(_np(theta), list(dims), _np(obs))
+        th = _np(theta)
+        if precision in ("bf16", "bf16s"):
+            row = th if precision == "bf16" else self._exact_biases(orc.round_bf16(th).copy(), th, list(dims))
+            out = orc.mlp_forward_bf16(row, list(dims), _np(obs))
+        else:
+            out = orc.mlp_forward(th, list(dims), _np(obs))
         ret_out[0] = float(orc.synthetic_return(out, _np(target)))
         if bc_out is not None:
             bc_out.copy_(torch.from_numpy(orc.synthetic_bc(out, bc_obs, bc_dim)))

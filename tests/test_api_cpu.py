@@ -373,3 +373,65 @@ def test_checkpoint_resume_hooks_mode(tmp_path):
     tb = torch.nn.utils.parameters_to_vector(b.policy.parameters()).detach().numpy()
     np.testing.assert_array_equal(ta, tb)             # incl. the SGD momentum buffers restored
     assert a.best_reward == b.best_reward
+
+
+# ------------------------------------------------------------------ folded post-update rollout (host logic)
+def _tc_es(log_interval, seen=None, n=16):
+    """Fused ES on the emulated tensor-core backend (bf16s): the only mode that folds."""
+    dims = [64, 64, 32]
+    g = torch.Generator().manual_seed(2)
+    obs, tgt = torch.randn(256, 64, generator=g), torch.randn(256, 32, generator=g)
+
+    class Q(E.ES):
+        def log(self):
+            if seen is not None:
+                seen.append((self.step, self.episode_reward, self.best_reward))
+    torch.manual_seed(4)
+    be = OracleBackend(tensor_core=True)
+    es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=n, sigma=0.02, policy_kwargs={"dims": dims},
+           agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 14,
+           log_interval=log_interval, _backend=be)
+    assert es._fused and es._precision == "bf16s"
+    return es, be
+
+
+def test_deferred_post_update_rollout_is_equivalent_cpu():
+    """estorch.py:181-185 runs one rollout of the updated policy per generation.  With
+    log_interval > 1 that rollout is folded into the next generation's evaluate launch;
+    everything observable must equal the log_interval = 1 run."""
+    out = {}
+    for li in (1, 3):
+        seen = []
+        es, be = _tc_es(li, seen)
+        es.train(n_steps=7)
+        out[li] = dict(theta=es._slots[0].theta.clone(), best=es._slots[0].best_theta.clone(), seen=seen,
+                       ep=es.episode_reward, br=es.best_reward, ret=es.population_returns.copy(), folds=be.centre_folds)
+    a, b = out[1], out[3]
+    assert a["folds"] == 0 and b["folds"] == 4          # generations 0, 1, 3, 4 defer; 2, 5 log; 6 is the last
+    assert torch.equal(a["theta"], b["theta"]) and torch.equal(a["best"], b["best"])
+    assert a["ep"] == b["ep"] and a["br"] == b["br"]
+    np.testing.assert_array_equal(a["ret"], b["ret"])
+    assert [s for s, _, _ in b["seen"]] == [2, 5] and len(a["seen"]) == 7
+    for step, ep, br in b["seen"]:
+        assert (step, ep, br) == a["seen"][step]
+
+
+def test_observing_mid_training_flushes_the_deferred_rollout():
+    """Reading episode_reward / best_reward / state_dict() while a rollout is still deferred
+    runs it first (nobody may see the previous generation's value)."""
+    ref, _ = _tc_es(1)
+    ref.train(n_steps=1)
+    es, be = _tc_es(100)
+    es.n_steps, es.step = 10, 0
+    es._fused_generation(es._slots[0])            # what _master does for one generation
+    assert es._pending_centre
+    assert es.episode_reward == ref.episode_reward and not es._pending_centre
+    assert es.best_reward == ref.best_reward
+    es.step += 1; es._generation += 1             # ... and what it does after it
+    es._fused_generation(es._slots[0])
+    assert es._pending_centre and be.centre_folds == 0
+    sd = es.state_dict()
+    assert not es._pending_centre
+    ref.train(n_steps=1)                           # a second generation (the generation counter keeps running)
+    assert sd["slots"][0]["state"]["episode_reward"] == ref.episode_reward
+    assert torch.equal(sd["slots"][0]["theta"], ref._slots[0].theta)
