@@ -55,8 +55,8 @@ namespace {
 constexpr int kMaxW = 512;            // max layer width (K and N) of this path
 constexpr int kBlockK = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int kKBlockBytes = 128 * kBlockK * 2;   // one [128 x 64] bf16 tile = 16 KB
-constexpr int kSubPerStage = 1;                   // k-blocks per ring stage (2 was measured: no gain, less ring depth)
-constexpr int kStageBytes = kSubPerStage * kKBlockBytes;   // B ring stage: [<=128 rows x 64] per k-block at CG=2
+constexpr int kStageBytes = kKBlockBytes;          // B ring stage = one k-block: [<=128 rows x 64] at CG=2
+                                                   // (two k-blocks per stage were measured: no gain, less ring depth)
 constexpr int kNumEpiWarps = 4, kNumProdWarps = 8;
 // the producer warps form groups that work on different ring stages concurrently:
 // fp32 sources: 2 groups of 4 warps (theta and noise both through registers);
@@ -315,7 +315,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
   uint64_t* bar_tma = bars + 2 * kStages + 3;    // [kStages] theta tile landed in the ring slot (local, bf16s only)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 3);
   float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kNumEpiWarps]
-  int* s_prog = reinterpret_cast<int*>(s_loss + kNumEpiWarps);   // n-groups started by the producers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -323,7 +322,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
   const int L = p.desc.n_layers;
 
   if (warp == 0 && lane == 0) {
-    *s_prog = 0;
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(bar_full + s), CG * kProdGroupWarps);
       mbar_init(smem_u32(bar_empty + s), 1);
@@ -376,7 +374,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             const int Ng = min(256, N - n0);
             const uint32_t idesc = make_idesc(128 * CG, Ng);
             const uint32_t tmem_d = tmem_base + (uint32_t)n0;
-            for (int kb = 0; kb < K / kBlockK; kb += kSubPerStage) {
+            for (int kb = 0; kb < K / kBlockK; ++kb) {
               if (kb >= 4 && !second_half_ready) {   // k-blocks 4..7 (and TMEM columns >= 256 drained)
                 const long long th1 = PROF_T();
                 mbar_wait(smem_u32(bar_h), h_phase);
@@ -385,25 +383,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
                 tc_fence_after();
                 second_half_ready = true;
               }
-              const int nsub = min(kSubPerStage, K / kBlockK - kb);
               const long long tf0 = PROF_T();
               mbar_wait(smem_u32(bar_full + stage), ring_phase);
               PROF_ADD(2, tf0);
               const long long ti0 = PROF_T();
               tc_fence_after();
               if (elect_one()) {
-                for (int sub = 0; sub < nsub; ++sub) {
-                  const uint32_t a_addr = smem_u32(sH + (kb + sub) * kKBlockBytes);
-                  const uint32_t b_addr = smem_u32(sB + stage * kStageB + sub * kKBlockBytes);
+                const uint32_t a_addr = smem_u32(sH + kb * kKBlockBytes);
+                const uint32_t b_addr = smem_u32(sB + stage * kStageB);
 #pragma unroll
-                  for (int k = 0; k < kBlockK / 16 && !(p.dbg & 4); ++k) {
-                    const uint64_t da = make_sw128_desc(a_addr + k * 32);
-                    const uint64_t db = make_sw128_desc(b_addr + k * 32);
-                    umma_bf16<CG>(tmem_d, da, db, idesc, (kb | sub | k) != 0 ? 1u : 0u);
-                  }
+                for (int k = 0; k < kBlockK / 16 && !(p.dbg & 4); ++k) {
+                  const uint64_t da = make_sw128_desc(a_addr + k * 32);
+                  const uint64_t db = make_sw128_desc(b_addr + k * 32);
+                  umma_bf16<CG>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                 }
                 umma_commit<CG>(smem_u32(bar_empty + stage));          // frees the ring slot (both CTAs)
-                if (kb + nsub == K / kBlockK) {
+                if (kb + 1 == K / kBlockK) {
                   if (n0 + 256 >= N) umma_commit<CG>(smem_u32(bar_acc));     // layer accumulated
                   else umma_commit<CG>(smem_u32(bar_acc0));                  // tile 0 of 2: its drain overlaps tile 1's MMAs
                 }
@@ -650,7 +645,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
     const int pgroup = pwarp / kProdGroupWarps;
     const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // thread index inside the group
     constexpr int kPT = 32 * kProdGroupWarps;
-    struct StageDesc { const float* th; const float* ep; const uint16_t* th16; const uint16_t* ep16; int K; int n_items; int sub_items; float ssig; };
+    struct StageDesc { const float* th; const float* ep; const uint16_t* th16; const uint16_t* ep16; int K; int n_items; float ssig; };
     constexpr bool src16 = S16;
     int cached_task = -1;
     const float* cached_trow = p.theta;
@@ -674,13 +669,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       d.th16 = p.theta16 + rbase;
       d.ep16 = cached_trow16 + rbase;
       d.K = K;
-      d.sub_items = rows * 8;                                  // 16-byte output chunks per k-block
-      d.n_items = (kSubPerStage > 1) ? d.sub_items * min(kSubPerStage, K / kBlockK - kb) : d.sub_items;
+      d.n_items = rows * 8;                                    // 16-byte output chunks of the stage
       d.ssig = cached_ssig;
     };
     auto advance = [&](int& task, int& l, int& n0, int& kb) -> bool {
-      kb += kSubPerStage;
-      if (kb >= lay[l].K / kBlockK) {
+      if (++kb >= lay[l].K / kBlockK) {
         kb = 0;
         n0 += 256;
         if (n0 >= lay[l].N) {
@@ -710,9 +703,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
         // threads streams the noise: 16 items (128-bit loads, 8 elements each) per thread
         // cover the whole [128 x 64] stage, issued before the slot is even free.
         // item u of a thread = tile row u*8 + r0, 16-byte chunk c0 of the 128-byte row
-        static_assert(kSubPerStage == 1 && kPT == 64, "bf16s producer: 64-thread groups, one k-block per stage");
+        static_assert(kPT == 64, "bf16s producer: 64-thread groups");
         const int r0 = ptid >> 3, c0 = ptid & 7;
-        const int rows = cur.sub_items >> 3;
+        const int rows = cur.n_items >> 3;
         const uint16_t* eptr = cur.ep16 + (size_t)r0 * cur.K + c0 * 8;
         uint4 e16[16];
 #pragma unroll
@@ -748,8 +741,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           for (int u = 0; u < 4; ++u) {
             const int it = it0 + u * kPT + ptid;
             if (it < cur.n_items && !(p.dbg & 1)) {
-              const int sub = (kSubPerStage > 1) ? (it >= cur.sub_items) : 0, iq = it - sub * cur.sub_items;
-              const int64_t off = (int64_t)(iq >> 3) * cur.K + sub * kBlockK + (iq & 7) * 8;
+              const int64_t off = (int64_t)(it >> 3) * cur.K + (it & 7) * 8;
               th[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off));
               th[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off + 4));
               ep[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.ep + off));
@@ -773,8 +765,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
               const uint32_t w1 = pack_bf16(fmaf(sg, ep[u][0].z, th[u][0].z), fmaf(sg, ep[u][0].w, th[u][0].w));
               const uint32_t w2 = pack_bf16(fmaf(sg, ep[u][1].x, th[u][1].x), fmaf(sg, ep[u][1].y, th[u][1].y));
               const uint32_t w3 = pack_bf16(fmaf(sg, ep[u][1].z, th[u][1].z), fmaf(sg, ep[u][1].w, th[u][1].w));
-              const int sub = (kSubPerStage > 1) ? (it >= cur.sub_items) : 0, iq = it - sub * cur.sub_items;
-              st_shared_v4(sbase + sub * kKBlockBytes + sw128_offset(iq >> 3, iq & 7), w0, w1, w2, w3);
+              st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
             }
           }
           if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
