@@ -17,6 +17,18 @@ from test_api_cpu import MLP, _load_theta  # noqa: E402
 
 def main():
     out_dir, algo = sys.argv[1], sys.argv[2]
+    if algo == "es_fold":
+        # bf16s on the emulated tensor-core backend, log_interval 3: the post-update rollout of
+        # most generations rides in the next generation's evaluate launch, on every rank
+        from test_api_cpu import _tc_es
+        seen = []
+        es, be = _tc_es(3, seen)
+        es.train(n_steps=5)
+        np.savez(os.path.join(out_dir, f"rank{es.rank}.npz"), theta=es._slots[0].theta.numpy(),
+                 best=es._slots[0].best_theta.numpy(), step=es.step, n_logs=len(seen), folds=be.centre_folds,
+                 returns=es.population_returns, world=es.n_workers, pairs_local=es._pairs_local,
+                 pair_begin=es._pair_begin, episode=es.episode_reward, best_reward=es.best_reward)
+        return
     g = np.load(os.path.join(ROOT, "tests", "golden",
                              "es_cartpole_p64.npz" if algo == "es" else "nsra_bipedal_p32.npz"))
     dims = [int(d) for d in g["dims"]]

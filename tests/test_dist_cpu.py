@@ -54,3 +54,20 @@ def test_world2_nsra_sharded_generation(tmp_path):
     r0, r1 = _run(2, "nsra", tmp_path)
     np.testing.assert_array_equal(r0["theta"], r1["theta"])
     assert rel_err(r0["returns"][:, 1], g["returns"][1][:, 1]) < 1e-4
+
+
+def test_world2_folded_post_update_rollout(tmp_path):
+    """The deferred post-update rollout (folded into the next generation's evaluate launch) on a
+    sharded population: ranks stay bit-identical and agree with the single-process run up to the
+    fp32 summation order of the all-reduced gradient."""
+    from test_api_cpu import _tc_es
+    r0, r1 = _run(2, "es_fold", tmp_path)
+    assert int(r0["world"]) == 2 and int(r0["pairs_local"]) == 4 and int(r1["pair_begin"]) == 4
+    assert int(r0["folds"]) == 3 and int(r1["folds"]) == 3       # generations 0, 1, 3 defer; 2 logs; 4 is the last
+    assert int(r0["n_logs"]) == 1 and int(r1["n_logs"]) == 0
+    for k in ("theta", "best", "returns", "episode", "best_reward"):
+        np.testing.assert_array_equal(r0[k], r1[k])
+    es, _ = _tc_es(3)
+    es.train(n_steps=5)
+    assert rel_err(r0["theta"], es._slots[0].theta.numpy()) < 1e-5
+    assert abs(float(r0["episode"]) - es.episode_reward) < 1e-5 * abs(es.episode_reward)
