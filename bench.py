@@ -196,7 +196,7 @@ def run_ours(args, wl, rank, world, local_rank):
     es = Bench(MLP, Streaming, torch.optim.Adam, population_size=P, sigma=sigma,
                policy_kwargs={"dims": dims}, agent_kwargs=dict(obs=obs, target=tgt),
                optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << args.table_log2, noise_seed=42,
-               log_interval=10 ** 9)
+               log_interval=10 ** 9, eval_precision=args.eval_precision)
     assert es._fused, "bench: fused device path is not active"
     be = es._be
 
@@ -311,7 +311,10 @@ def run_ours(args, wl, rank, world, local_rank):
             "unit": "generations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": {"bf16": "bf16 operands / f32 accumulate (evaluate GEMMs); f32 noise, ranks, reduction, Adam",
+            "dtype": {"f16": "f32 (fp32-equivalent: evaluate GEMMs on tcgen05 with fp16 operands = 11-bit significand, "
+                             "TF32 class, each weight formed in fp32 from fp32 theta + the exactly-16-bit noise value and "
+                             "rounded once, f32 accumulate, f32 bias/loss; f32 ranks, reduction, Adam)",
+                      "bf16": "bf16 operands / f32 accumulate (evaluate GEMMs); f32 noise, ranks, reduction, Adam",
                       "bf16s": "bf16 operands formed from bf16 shadows of theta/noise, f32 accumulate (evaluate "
                                "GEMMs); f32 noise table, ranks, reduction, Adam"}.get(es._precision, "f32"),
             "data": "synthetic", "config": workload_config(args, wl, world),
@@ -344,7 +347,7 @@ def main():
     ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
     ap.add_argument("--table-log2", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--eval-precision", default="auto", choices=["auto", "fp32", "bf16", "bf16s"])
+    ap.add_argument("--eval-precision", default="auto", choices=["auto", "fp32", "f16", "bf16", "bf16s"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -58,6 +58,11 @@ SIGNATURES = {
     "estk_eval_mlp_bf16s": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _P, _P, _I32, _F32, _P, _P, _I32,
                             _P, _P, _P, _P, _I32, _I32, _P, _P],
     "estk_eval_mlp_center_bf16s": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _I32, _P, _P, _I32, _I32, _P],
+    "estk_shadow_f16": [_P, _P, _P, _I64, _P, _P],
+    "estk_eval_mlp_f16": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _P, _P, _I32, _F32, _P, _P, _I32,
+                          _P, _P, _P, _P, _I32, _I32, _P, _P],
+    "estk_eval_mlp_center_f16": [_P, C.POINTER(EstkMlpDesc), _P, _P, _P, _I32, _P, _P, _I32, _I32, _P],
+    "estk_eval_mlp_f16_supported": [C.POINTER(EstkMlpDesc), _I32],
     "estk_eval_conv_vbn_scratch_bytes": [_P, _I32, _I32],
     "estk_eval_conv_vbn": [_P, _I32, _P, _P, _P, _P, _I32, _F32, _P, _I32, _P, _P, _I32, _P, _P, _P, _I64, _P],
     "estk_track_best": [_P, _P, _P, _P, _P, _I64, _P],

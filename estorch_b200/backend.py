@@ -147,6 +147,22 @@ class CudaBackend:
         d = mlp_desc(dims)
         return bool(self.lib.estk_eval_mlp_bf16_supported(C.byref(d), int(B)))
 
+    def eval_supports_f16(self, dims, B) -> bool:
+        d = mlp_desc(dims)
+        return bool(self.lib.estk_eval_mlp_f16_supported(C.byref(d), int(B)))
+
+    def shadow_f16(self, src, dst, check=True) -> int:
+        """dst (float16, same numel) = src; returns how many entries were NOT exactly
+        representable (0 for tables made by fill_noise_table).  ``check`` reads the
+        counter back (one host synchronisation; setup time only)."""
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device) if check else None
+        _capi.check(self.lib.estk_shadow_f16(self._ctx, self._ptr(src, torch.float32, "src"),
+                                             self._ptr(dst, torch.float16, "dst"), src.numel(),
+                                             self._ptr(cnt, torch.int64, "inexact"), self._stream()),
+                    "estk_shadow_f16")
+        self.launches += 1
+        return int(cnt.item()) if check else 0
+
     def shadow_bf16(self, src, dst):
         """dst (int16/bfloat16 storage, same numel) = bf16(src)."""
         _capi.check(self.lib.estk_shadow_bf16(self._ctx, self._ptr(src, torch.float32, "src"),
@@ -166,13 +182,18 @@ class CudaBackend:
                   self._ptr(ret_minus, torch.float32, "ret_minus"), self._ptr(bc_plus, torch.float32, "bc_plus"),
                   self._ptr(bc_minus, torch.float32, "bc_minus"), int(bc_obs), int(bc_dim))
         stream = (self._stream(),)
-        if precision in ("bf16", "bf16s"):
+        if precision in ("f16", "bf16", "bf16s"):
             stream = (self._ptr(centre_out, torch.float32, "centre_out"), self._stream())
         elif centre_out is not None:
             raise ValueError("centre_out (folded post-update rollout) needs a tensor-core precision mode")
         common = common + stream
         th, tb = self._ptr(theta, torch.float32, "theta"), self._ptr(table, torch.float32, "table")
-        if precision == "bf16s":
+        if precision == "f16":
+            if table16 is None:
+                raise ValueError("precision='f16' needs table16, the exact fp16 copy of the table (see shadow_f16)")
+            rc = self.lib.estk_eval_mlp_f16(self._ctx, C.byref(d), th, tb,
+                                            self._ptr(table16, torch.float16, "table16"), *common)
+        elif precision == "bf16s":
             if theta16 is None or table16 is None:
                 raise ValueError("precision='bf16s' needs theta16 and table16 (see shadow_bf16)")
             rc = self.lib.estk_eval_mlp_bf16s(self._ctx, C.byref(d), th, self._ptr(theta16, torch.bfloat16, "theta16"),
@@ -193,7 +214,9 @@ class CudaBackend:
                 int(obs.shape[0]), self._ptr(ret_out, torch.float32, "ret_out"),
                 self._ptr(bc_out, torch.float32, "bc_out"), int(bc_obs), int(bc_dim), self._stream())
         th = self._ptr(theta, torch.float32, "theta")
-        if precision == "bf16s":
+        if precision == "f16":
+            rc = self.lib.estk_eval_mlp_center_f16(self._ctx, C.byref(d), th, *tail)
+        elif precision == "bf16s":
             rc = self.lib.estk_eval_mlp_center_bf16s(self._ctx, C.byref(d), th,
                                                      self._ptr(theta16, torch.bfloat16, "theta16"), *tail)
         elif precision == "bf16":

@@ -45,6 +45,7 @@
 #include "estk_common.cuh"
 #include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -61,7 +62,15 @@ constexpr int kNumEpiWarps = 4, kNumProdWarps = 8;
 // the producer warps form groups that work on different ring stages concurrently:
 // fp32 sources: 2 groups of 4 warps (theta and noise both through registers);
 // bf16 shadows: 4 groups of 2 warps (theta tile by TMA, only the noise through registers)
-__host__ __device__ constexpr int prod_groups(bool s16) { return s16 ? 4 : 2; }
+__host__ __device__ constexpr int prod_groups(int mode) { return mode == 1 ? 4 : 2; }
+// operand / source modes of the kernel template:
+//   kModeBF16   bf16 operands formed from fp32 theta + fp32 table (through registers)
+//   kModeBF16S  bf16 operands formed from bf16 shadows (theta tile by TMA, in place)
+//   kModeF16    fp16 operands (11-bit significand = TF32 class) formed from fp32 theta and the EXACT
+//               16-bit copy of the noise table (estk_shadow_f16: table values are fp16-representable),
+//               one rounding per weight: W16 = rn_f16(theta + s*sigma*eps) with the sum in fp32;
+//               layer-0 input split x = x_hi + x_lo (two fp16 k-block sets, same B tile)
+constexpr int kModeBF16 = 0, kModeBF16S = 1, kModeF16 = 2;
 constexpr int kThreadsTC = 32 * (2 + kNumEpiWarps + kNumProdWarps);   // 448
 
 // TMA descriptors of the bf16 theta shadow, one per (layer, N tile): [N x K] row-major,
@@ -92,6 +101,7 @@ struct EvalTCParams {
   int n_centre;            // number of leading centre tasks (0 or chunks)
   int n_tasks;             // n_centre + pairs * n_signs * chunks
   int n_signs;             // 2, or 1 for the centre evaluation
+  int mode;                // kModeBF16 / kModeBF16S / kModeF16
   int dbg;                 // ESTK_TC_DEBUG bit mask (perf triage only): 1 no producer loads, 4 no MMA, 8 role counters, 16 TMEM read only
 };
 
@@ -240,8 +250,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 }
 // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
 // K-major A and B, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// (a/b format 0 = F16, 1 = BF16)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, bool f16) {
+  const uint32_t fmt = f16 ? 0u : ((1u << 7) | (1u << 10));
+  return (1u << 4) | fmt | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // byte offset of the 16-byte chunk (row r, chunk c8 of 8 bf16) inside a swizzled [rows x 64] tile
 __device__ __forceinline__ uint32_t sw128_offset(int r, int c8) {
@@ -257,6 +269,26 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+// fp16 variants (saturating: an activation beyond +-65504 becomes +-65504, not inf)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t h2) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&h2));
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack16_relu(float lo, float hi) {
+  return F16 ? pack_f16_relu(lo, hi) : pack_bf16_relu(lo, hi);
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -295,11 +327,12 @@ __device__ __forceinline__ TaskId decode_task(const EvalTCParams& p, int task, b
 
 // 448 threads at 128 registers: the register file is allocated per 4 warps, so a 14-warp
 // block is charged as 16 warps and 144 registers per thread do not launch (measured)
-template <int CG, bool S16, int RING>
+template <int CG, int MODE, int RING>
 __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTCParams p,
                                                                      const __grid_constant__ TcMaps maps) {
   constexpr int kStages = RING;
-  constexpr int kProdGroups = prod_groups(S16), kProdGroupWarps = kNumProdWarps / kProdGroups;
+  constexpr bool S16 = (MODE == kModeBF16S), F16 = (MODE == kModeF16);
+  constexpr int kProdGroups = prod_groups(MODE), kProdGroupWarps = kNumProdWarps / kProdGroups;
   constexpr int kStageB = (CG == 2) ? kStageBytes : 2 * kStageBytes;   // up to 256 rows at CG=1
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -372,8 +405,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           bool second_half_ready = (K <= 256) || (l == 0);   // hidden inputs wider than 256 arrive in two halves
           for (int n0 = 0; n0 < N; n0 += 256) {
             const int Ng = min(256, N - n0);
-            const uint32_t idesc = make_idesc(128 * CG, Ng);
+            const uint32_t idesc = make_idesc(128 * CG, Ng, F16);
             const uint32_t tmem_d = tmem_base + (uint32_t)n0;
+            // fp16 mode: the layer-0 input is x_hi + x_lo; the lo half lives K/64 k-blocks further
+            const int lo_kb = (F16 && l == 0) ? K / kBlockK : 0;
             for (int kb = 0; kb < K / kBlockK; ++kb) {
               if (kb >= 4 && !second_half_ready) {   // k-blocks 4..7 (and TMEM columns >= 256 drained)
                 const long long th1 = PROF_T();
@@ -396,6 +431,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
                   const uint64_t da = make_sw128_desc(a_addr + k * 32);
                   const uint64_t db = make_sw128_desc(b_addr + k * 32);
                   umma_bf16<CG>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                if (lo_kb) {
+                  const uint32_t a_lo = smem_u32(sH + (kb + lo_kb) * kKBlockBytes);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16 && !(p.dbg & 4); ++k)
+                    umma_bf16<CG>(tmem_d, make_sw128_desc(a_lo + k * 32), make_sw128_desc(b_addr + k * 32), idesc, 1u);
                 }
                 umma_commit<CG>(smem_u32(bar_empty + stage));          // frees the ring slot (both CTAs)
                 if (kb + 1 == K / kBlockK) {
@@ -476,8 +517,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           for (int u = 0; u < 8; ++u) {
             const int c = c0 + u;
             const uint32_t addr = smem_u32(sH + (c >> 3) * kKBlockBytes) + sw128_offset(row, c & 7);
-            st_shared_v4(addr, pack_bf16(x[u][0].x, x[u][0].y), pack_bf16(x[u][0].z, x[u][0].w),
-                         pack_bf16(x[u][1].x, x[u][1].y), pack_bf16(x[u][1].z, x[u][1].w));
+            const uint32_t h0 = pack16<F16>(x[u][0].x, x[u][0].y), h1 = pack16<F16>(x[u][0].z, x[u][0].w);
+            const uint32_t h2 = pack16<F16>(x[u][1].x, x[u][1].y), h3 = pack16<F16>(x[u][1].z, x[u][1].w);
+            st_shared_v4(addr, h0, h1, h2, h3);
+            if constexpr (F16) {
+              // x_lo = rn_f16(x - x_hi): the observation enters layer 0 with ~22 significant bits
+              const float2 f0 = unpack_f16(h0), f1 = unpack_f16(h1), f2 = unpack_f16(h2), f3 = unpack_f16(h3);
+              const uint32_t alo = smem_u32(sH + ((c >> 3) + K0 / kBlockK) * kKBlockBytes) + sw128_offset(row, c & 7);
+              st_shared_v4(alo, pack_f16(x[u][0].x - f0.x, x[u][0].y - f0.y), pack_f16(x[u][0].z - f1.x, x[u][0].w - f1.y),
+                           pack_f16(x[u][1].x - f2.x, x[u][1].y - f2.y), pack_f16(x[u][1].z - f3.x, x[u][1].w - f3.y));
+            }
           }
         }
       }
@@ -512,8 +561,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 t = ld_shared_v4(baddr + g * 16);
-            pk[g * 2 + 0] = pack_bf16_relu(__uint_as_float(v[g * 4 + 0]) + t.x, __uint_as_float(v[g * 4 + 1]) + t.y);
-            pk[g * 2 + 1] = pack_bf16_relu(__uint_as_float(v[g * 4 + 2]) + t.z, __uint_as_float(v[g * 4 + 3]) + t.w);
+            pk[g * 2 + 0] = pack16_relu<F16>(__uint_as_float(v[g * 4 + 0]) + t.x, __uint_as_float(v[g * 4 + 1]) + t.y);
+            pk[g * 2 + 1] = pack16_relu<F16>(__uint_as_float(v[g * 4 + 2]) + t.z, __uint_as_float(v[g * 4 + 3]) + t.w);
           }
         };
         // W packed words (2*W output features starting at feature f0) -> activations in smem
@@ -658,7 +707,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
         const int j = (!tk.centre && p.order) ? p.order[tk.slot] : tk.slot;
         const int64_t off_j = tk.centre ? 0 : p.offsets[j];
         cached_trow = tk.centre ? p.theta : p.table + off_j;
-        cached_trow16 = tk.centre ? p.theta16 : p.table16 + off_j;
+        cached_trow16 = tk.centre ? (F16 ? nullptr : p.theta16) : p.table16 + off_j;
         cached_ssig = tk.centre ? 0.f : (tk.sgn ? -p.sigma : p.sigma);
       }
       const int K = lay[l].K;
@@ -667,7 +716,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       d.th = p.theta + rbase;
       d.ep = cached_trow + rbase;
       d.th16 = p.theta16 + rbase;
-      d.ep16 = cached_trow16 + rbase;
+      d.ep16 = cached_trow16 ? cached_trow16 + rbase : nullptr;
       d.K = K;
       d.n_items = rows * 8;                                    // 16-byte output chunks of the stage
       d.ssig = cached_ssig;
@@ -734,6 +783,45 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           }
         }
         if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
+      } else if constexpr (F16) {
+        // fp32 theta + the exact fp16 copy of the noise row, both through registers:
+        // W = rn_f16(theta + s*sigma*eps), the sum formed in fp32 (one rounding per weight)
+        for (int it0 = 0; it0 < cur.n_items; it0 += 4 * kPT) {
+          uint4 e16[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * kPT + ptid;
+            e16[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (it < cur.n_items && !(p.dbg & 1)) {
+              const int64_t off = (int64_t)(it >> 3) * cur.K + (it & 7) * 8;
+              th[u][0] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off));
+              th[u][1] = ld_noise4(reinterpret_cast<const float4*>(cur.th + off + 4));
+              if (cur.ep16) e16[u] = ld_noise4u(reinterpret_cast<const uint4*>(cur.ep16 + off));
+            }
+          }
+          if (!waited) {
+            const long long tw0 = pprof ? clock64() : 0ll;
+            mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
+            waited = true;
+            if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
+          }
+          const long long tc0 = pprof ? clock64() : 0ll;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * kPT + ptid;
+            if (it < cur.n_items) {
+              const float sg = cur.ssig;
+              const float2 e0 = unpack_f16(e16[u].x), e1 = unpack_f16(e16[u].y);
+              const float2 e2 = unpack_f16(e16[u].z), e3 = unpack_f16(e16[u].w);
+              const uint32_t w0 = pack_f16(fmaf(sg, e0.x, th[u][0].x), fmaf(sg, e0.y, th[u][0].y));
+              const uint32_t w1 = pack_f16(fmaf(sg, e1.x, th[u][0].z), fmaf(sg, e1.y, th[u][0].w));
+              const uint32_t w2 = pack_f16(fmaf(sg, e2.x, th[u][1].x), fmaf(sg, e2.y, th[u][1].y));
+              const uint32_t w3 = pack_f16(fmaf(sg, e3.x, th[u][1].z), fmaf(sg, e3.y, th[u][1].w));
+              st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
+            }
+          }
+          if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
+        }
       } else {
       for (int it0 = 0; it0 < cur.n_items; it0 += 4 * kPT) {
           // every 128-bit load of the batch is issued up front (16 in flight per thread) ...
@@ -796,10 +884,10 @@ size_t tc_smem_bytes(int stages) {
          (3 * stages + 3) * sizeof(uint64_t) + 128;
 }
 
-template <int CG, bool S16, int RING>
+template <int CG, int MODE, int RING>
 int launch_tc(estk_ctx* ctx, EvalTCParams& p, const TcMaps* maps, cudaStream_t stream) {
   const size_t smem = tc_smem_bytes<CG>(RING);
-  ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_tc_kernel<CG, S16, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_tc_kernel<CG, MODE, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int clusters = ctx->sm_count / CG;
   if (clusters > p.n_tasks) clusters = p.n_tasks;
   cudaLaunchConfig_t cfg = {};
@@ -814,7 +902,7 @@ int launch_tc(estk_ctx* ctx, EvalTCParams& p, const TcMaps* maps, cudaStream_t s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_tc_kernel<CG, S16, RING>, p, *maps));
+  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_tc_kernel<CG, MODE, RING>, p, *maps));
   return ESTK_OK;
 }
 
@@ -869,7 +957,10 @@ int build_theta_maps(const estk_mlp_desc& d, const uint16_t* theta16, int cg, Tc
   return ESTK_OK;
 }
 
-int tc_supported(const estk_mlp_desc& d, int B, int cg, const char** why) {
+int tc_supported(const estk_mlp_desc& d, int B, int cg, const char** why, int mode = kModeBF16) {
+  if (mode == kModeF16 && d.n_layers >= 1 && 2 * d.dims[0] > kMaxW) {
+    *why = "fp16 mode splits the observations into hi + lo halves: input width <= 256"; return 0;
+  }
   if (d.n_layers < 1 || d.n_layers > ESTK_MAX_LAYERS) { *why = "n_layers"; return 0; }
   if (d.activation != 0) { *why = "activation"; return 0; }
   for (int l = 0; l < d.n_layers; ++l) {
@@ -884,7 +975,7 @@ int tc_supported(const estk_mlp_desc& d, int B, int cg, const char** why) {
 int run_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream, const char* who) {
   const char* why = "";
   const int cg = 2;
-  if (!tc_supported(p.desc, p.B, cg, &why)) {
+  if (!tc_supported(p.desc, p.B, cg, &why, p.mode)) {
     estk_set_error("%s: shape not supported by the tcgen05 path (%s)", who, why);
     return ESTK_ERR_UNSUPPORTED;
   }
@@ -901,12 +992,14 @@ int run_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream, const char* who)
   // 128 KB of activations (ESTK_TC_RING=4|5 overrides; perf triage only)
   static const int ring_env = [] { const char* e = getenv("ESTK_TC_RING"); return e ? atoi(e) : 0; }();
   static thread_local TcMaps maps;
+  if (p.mode == kModeF16)
+    return ring_env == 4 ? launch_tc<2, kModeF16, 4>(ctx, p, &maps, stream) : launch_tc<2, kModeF16, 5>(ctx, p, &maps, stream);
   if (p.theta16) {
     const int rc = build_theta_maps(p.desc, p.theta16, cg, &maps);
     if (rc != ESTK_OK) return rc;
-    return ring_env == 4 ? launch_tc<2, true, 4>(ctx, p, &maps, stream) : launch_tc<2, true, 5>(ctx, p, &maps, stream);
+    return ring_env == 4 ? launch_tc<2, kModeBF16S, 4>(ctx, p, &maps, stream) : launch_tc<2, kModeBF16S, 5>(ctx, p, &maps, stream);
   }
-  return ring_env == 5 ? launch_tc<2, false, 5>(ctx, p, &maps, stream) : launch_tc<2, false, 4>(ctx, p, &maps, stream);
+  return ring_env == 5 ? launch_tc<2, kModeBF16, 5>(ctx, p, &maps, stream) : launch_tc<2, kModeBF16, 4>(ctx, p, &maps, stream);
 }
 
 }  // namespace
@@ -985,7 +1078,7 @@ extern "C" int estk_eval_mlp_bf16s(estk_ctx* ctx, const estk_mlp_desc* desc, con
   p.pairs = pairs; p.sigma = sigma; p.obs = obs; p.target = target; p.B = B;
   p.ret_plus = returns_plus; p.ret_minus = returns_minus;
   p.bc_plus = bc_plus; p.bc_minus = bc_minus; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
-  p.n_signs = 2; p.centre_out = centre_return_out;
+  p.n_signs = 2; p.centre_out = centre_return_out; p.mode = kModeBF16S;
   return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_bf16s");
 }
 
@@ -1000,8 +1093,79 @@ extern "C" int estk_eval_mlp_center_bf16s(estk_ctx* ctx, const estk_mlp_desc* de
   p.pairs = 1; p.sigma = 0.f; p.obs = obs; p.target = target; p.B = B;
   p.ret_plus = return_out; p.ret_minus = nullptr;
   p.bc_plus = bc_out; p.bc_minus = nullptr; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
-  p.n_signs = 1;
+  p.n_signs = 1; p.mode = kModeBF16S;
   return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_center_bf16s");
+}
+
+// ---- fp16 operands from fp32 theta + the exact 16-bit noise table (the default tensor-core mode)
+__global__ void __launch_bounds__(256) shadow_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4,
+                                                         unsigned long long* __restrict__ inexact) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = src[i];
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    bad += (fa.x != v.x) + (fa.y != v.y) + (fb.x != v.z) + (fb.y != v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a);
+    o.y = *reinterpret_cast<const uint32_t*>(&b);
+    dst[i] = o;
+  }
+  if (inexact && bad) atomicAdd(inexact, (unsigned long long)bad);
+}
+
+extern "C" int estk_shadow_f16(estk_ctx* ctx, const float* src, uint16_t* dst, int64_t n, uint64_t* inexact_count,
+                               void* stream) {
+  ESTK_CHECK_ARG(ctx && src && dst && n > 0 && (n % 4) == 0, "estk_shadow_f16: null argument or n not a multiple of 4");
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(src) && ((uintptr_t)dst & 7u) == 0, "estk_shadow_f16: unaligned buffers");
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  shadow_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src),
+                                                            reinterpret_cast<uint2*>(dst), n / 4,
+                                                            reinterpret_cast<unsigned long long*>(inexact_count));
+  ESTK_CUDA(cudaGetLastError());
+  return ESTK_OK;
+}
+
+extern "C" int estk_eval_mlp_f16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta, const float* table,
+                                 const uint16_t* table16, const int64_t* offsets, const int32_t* order, int32_t pairs,
+                                 float sigma, const float* obs, const float* target, int32_t B, float* returns_plus,
+                                 float* returns_minus, float* bc_plus, float* bc_minus, int32_t bc_obs,
+                                 int32_t bc_dim, float* centre_return_out, void* stream) {
+  ESTK_CHECK_ARG(ctx && desc && theta && table && table16 && offsets && obs && target && returns_plus && returns_minus,
+                 "estk_eval_mlp_f16: null argument");
+  ESTK_CHECK_ARG((bc_plus == nullptr) == (bc_minus == nullptr), "estk_eval_mlp_f16: bc_plus/bc_minus must both be set or both null");
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(table) && ESTK_ALIGNED16(obs) && ESTK_ALIGNED16(target) &&
+                 ESTK_ALIGNED16(table16), "estk_eval_mlp_f16: buffers must be 16-byte aligned");
+  EvalTCParams p = {};
+  p.desc = *desc; p.theta = theta; p.table = table; p.table16 = table16;
+  p.offsets = offsets; p.order = order;
+  p.pairs = pairs; p.sigma = sigma; p.obs = obs; p.target = target; p.B = B;
+  p.ret_plus = returns_plus; p.ret_minus = returns_minus;
+  p.bc_plus = bc_plus; p.bc_minus = bc_minus; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
+  p.n_signs = 2; p.centre_out = centre_return_out; p.mode = kModeF16;
+  return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_f16");
+}
+
+extern "C" int estk_eval_mlp_center_f16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                                        const float* obs, const float* target, int32_t B, float* return_out,
+                                        float* bc_out, int32_t bc_obs, int32_t bc_dim, void* stream) {
+  ESTK_CHECK_ARG(ctx && desc && theta && obs && target && return_out, "estk_eval_mlp_center_f16: null argument");
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(obs) && ESTK_ALIGNED16(target),
+                 "estk_eval_mlp_center_f16: buffers must be 16-byte aligned");
+  EvalTCParams p = {};
+  p.desc = *desc; p.theta = theta; p.table = theta; p.offsets = nullptr; p.order = nullptr;
+  p.pairs = 1; p.sigma = 0.f; p.obs = obs; p.target = target; p.B = B;
+  p.ret_plus = return_out; p.ret_minus = nullptr;
+  p.bc_plus = bc_out; p.bc_minus = nullptr; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
+  p.n_signs = 1; p.mode = kModeF16;
+  return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_center_f16");
+}
+
+extern "C" int estk_eval_mlp_f16_supported(const estk_mlp_desc* desc, int32_t B) {
+  const char* why = "";
+  return desc ? tc_supported(*desc, B, 2, &why, kModeF16) : 0;
 }
 
 extern "C" int estk_eval_mlp_bf16_supported(const estk_mlp_desc* desc, int32_t B) {

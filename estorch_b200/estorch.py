@@ -166,11 +166,15 @@ class ES:
         noise_seed: seed of the table and of the per-generation offsets.
         log_interval: call ``log()`` every k-th generation only (default 1 =
             reference behaviour).
-        eval_precision: arithmetic of the fused evaluate kernel: ``"fp32"`` (exact
-            CUDA-core path), ``"bf16"`` (tcgen05 tensor cores, bf16 operands, fp32
-            accumulation), ``"bf16s"`` (as bf16, with the weight producers reading bf16
-            shadows of theta and the noise table -- half the bytes) or ``"auto"``
-            (bf16s when the policy shape supports it, else fp32).
+        eval_precision: arithmetic of the fused evaluate kernel:
+            ``"fp32"``  CUDA-core path, fp32 throughout;
+            ``"f16"``   tcgen05 tensor cores with fp16 operands (11-bit significand, the
+                        TF32 class) and fp32 accumulation; every weight is formed in fp32
+                        from the fp32 theta and the (exactly 16-bit representable) noise
+                        value and rounded once; observations enter as hi + lo halves;
+            ``"auto"``  (default) ``"f16"`` when the policy shape supports it, else ``"fp32"``;
+            ``"bf16"`` / ``"bf16s"``  explicit opt-in, lower precision (8-bit significand;
+                        ``bf16s`` additionally reads bf16 shadows of theta and the table).
     Attributes as documented at estorch.py:108-117.
     """
 
@@ -211,18 +215,19 @@ class ES:
         self._is_conv = isinstance(self._spec, ConvVBNSpec)
         self._fused = self._decide_fused(optimizer)
         self._host_cache = {}
-        if eval_precision not in ("auto", "fp32", "bf16", "bf16s"):
-            raise ValueError("eval_precision must be 'auto', 'fp32', 'bf16' or 'bf16s'")
+        if eval_precision not in ("auto", "fp32", "f16", "bf16", "bf16s"):
+            raise ValueError("eval_precision must be 'auto', 'fp32', 'f16', 'bf16' or 'bf16s'")
         self._precision = "fp32"
         if self._fused and self._is_conv and eval_precision not in ("auto", "fp32"):
             raise ValueError("the conv + VirtualBatchNorm evaluate kernel is fp32 only")
         if self._fused and not self._is_conv and eval_precision != "fp32":
-            supported = getattr(self._be, "eval_supports_bf16", lambda d, b: False)(
-                self._spec.dims, self.agent.obs.shape[0])
-            if eval_precision in ("bf16", "bf16s") and not supported:
-                raise ValueError("eval_precision='bf16[s]' needs layer widths that are multiples of 64 (in) / "
-                                 "32 (out), at most 512, and a batch that is a multiple of 256")
-            self._precision = (eval_precision if eval_precision != "auto" else "bf16s") if supported else "fp32"
+            probe = "eval_supports_f16" if eval_precision in ("auto", "f16") else "eval_supports_bf16"
+            supported = getattr(self._be, probe, lambda d, b: False)(self._spec.dims, self.agent.obs.shape[0])
+            if eval_precision != "auto" and not supported:
+                raise ValueError(f"eval_precision={eval_precision!r} needs layer widths that are multiples of 64 "
+                                 "(in) / 32 (out), at most 512 (f16: input width at most 256), and a batch that "
+                                 "is a multiple of 256")
+            self._precision = ("f16" if eval_precision == "auto" else eval_precision) if supported else "fp32"
 
         # ---- noise table (replicated on every GPU, identical by construction)
         n_pad = (self.n_parameters + 31) // 32 * 32
@@ -231,9 +236,8 @@ class ES:
         self._table = self._be.alloc(size)
         self._be.fill_noise_table(self._table, self._noise_seed)
         self._table16 = None
-        if self._precision == "bf16s":
-            self._table16 = self._be.alloc(size, dtype=torch.bfloat16)
-            self._be.shadow_bf16(self._table, self._table16)
+        self._table16_version = None
+        self._ensure_table16()
 
         # ---- population bookkeeping
         P, W = self.population_size, self.n_workers
@@ -287,6 +291,8 @@ class ES:
         kw = self._optimizer_kwargs
         if kw.get("amsgrad") or kw.get("maximize") or kw.get("differentiable"):
             return False
+        if getattr(self, "k", 0) > 32:          # estk_knn_novelty's per-lane top-k buffer; the reference accepts
+            return False                        # any k (estorch.py:413) -> hooks mode (host novelty) serves it
         if self._is_conv:
             if self._ALGORITHM_TYPE != _Algorithm.classic:      # no behaviour characteristic on the conv kernel yet
                 return False
@@ -297,8 +303,8 @@ class ES:
                 tuple(self.agent.target.shape[1:]) != (self._spec.dims[-1],):
             return False
         hooks = ("_sample_policy", "_calculate_grad", "_calculate_returns", "_after_optimize",
-                 "_get_policy")
-        return not any(self._hook_overridden(h) for h in hooks)
+                 "_get_policy", "_calculate_novelty", "_rollout_bc")
+        return not any(hasattr(type(self), h) and self._hook_overridden(h) for h in hooks)
 
     # ------------------------------------------------------------------ reference API
     def terminate(self):
@@ -505,6 +511,29 @@ class ES:
         dist.all_gather_into_tensor(self._gather_buf.view(-1), loc.view(-1))
         t.view(2, W, pl).copy_(self._gather_buf.permute(1, 0, 2))     # member order: all +, then all -
 
+    def _sync_replicas(self):
+        """Every rank constructs its own policy / meta-population (torch's default seed
+        differs per process) while the reference keeps ONE master copy (estorch.py:136,
+        :401-408): rank 0's state is authoritative and is broadcast before the loop, so
+        that all ranks perturb the same centre and apply the same update."""
+        if self.n_workers == 1:
+            return
+        import torch.distributed as dist
+        for s_ in self._slots:
+            s_.push_theta()
+            for t in (s_.theta, s_.m, s_.v, s_.best_theta, s_.theta_prev, s_.state):
+                dist.broadcast(t, src=0)
+            if not s_.flattened:
+                torch.nn.utils.vector_to_parameters(
+                    s_.theta.detach().to(next(s_.module.parameters()).device).clone(), s_.module.parameters())
+        host = {k: getattr(self, k) for k in ("_archive", "_best_host", "weight", "t", "_generation")
+                if hasattr(self, k)}
+        box = [host]
+        dist.broadcast_object_list(box, src=0)
+        for k, v in box[0].items():
+            setattr(self, k, v)
+        self._host_cache = {}
+
     def _ensure_dist(self):
         if self.n_workers > 1:
             import torch.distributed as dist
@@ -519,24 +548,49 @@ class ES:
         g = optimizer.param_groups[0]
         return adam_desc(lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], clamp=1.0)
 
+    def _ensure_table16(self):
+        """16-bit copy of the noise table for the tensor-core evaluate modes: ``"f16"``
+        needs the EXACT fp16 copy (the table's entries are fp16-representable by
+        construction, estk_fill_noise_table), ``"bf16s"`` a rounded bf16 shadow.  Rebuilt
+        when the table was overwritten in place (``tensor._version``)."""
+        if self._precision not in ("f16", "bf16s"):
+            return
+        if self._table16 is not None and self._table16_version == self._table._version:
+            return
+        if self._precision == "f16":
+            if self._table16 is None:
+                self._table16 = self._be.alloc(self._table.numel(), dtype=torch.float16)
+            inexact = self._be.shadow_f16(self._table, self._table16)
+            if inexact:
+                raise ValueError(f"eval_precision='f16' needs a noise table whose entries are exactly "
+                                 f"fp16-representable ({inexact} are not); use the engine's own table or "
+                                 "eval_precision='fp32'")
+        else:
+            if self._table16 is None:
+                self._table16 = self._be.alloc(self._table.numel(), dtype=torch.bfloat16)
+            self._be.shadow_bf16(self._table, self._table16)
+        self._table16_version = self._table._version
+
     def _eval_kw(self, slot, centre=False):
-        """precision + (for "bf16s") refreshed bf16 shadows for the evaluate kernels."""
+        """precision + the 16-bit table copy (and, for "bf16s", a refreshed bf16 shadow of
+        theta) for the evaluate kernels."""
         kw = {"precision": self._precision}
         if self._precision == "bf16s":
             if slot.theta16 is None:
                 slot.theta16 = self._be.alloc(slot.n, dtype=torch.bfloat16)
             self._be.shadow_bf16(slot.theta, slot.theta16)
             kw["theta16"] = slot.theta16
-            if not centre:
-                if self._table16 is None:      # table was replaced after construction (tests)
-                    self._table16 = self._be.alloc(self._table.numel(), dtype=torch.bfloat16)
-                    self._be.shadow_bf16(self._table, self._table16)
-                kw["table16"] = self._table16
+        if self._precision in ("f16", "bf16s") and not centre:
+            self._ensure_table16()
+            kw["table16"] = self._table16
         return kw
 
     def _upload_batch(self):
         nb = self.agent.next_batch(self._generation)
         if nb is not None:
+            # a deferred post-update rollout belongs to the PREVIOUS batch (estorch.py:181-185
+            # runs it before the next generation samples): run it before the buffers change
+            self._flush_pending_centre()
             obs, tgt = nb
             self._obs.copy_(obs, non_blocking=True)
             self._tgt.copy_(tgt, non_blocking=True)
@@ -577,7 +631,7 @@ class ES:
         # post-update rollout (estorch.py:181-185).  It is a single 100 us task, so when nobody
         # can observe it before the next generation (no log() due, not the last generation) it
         # is deferred and folded into the next generation's evaluate launch.
-        if (self._precision in ("bf16", "bf16s") and not self._is_conv and not self._stop
+        if (self._precision in ("f16", "bf16", "bf16s") and not self._is_conv and not self._stop
                 and (self.step + 1) % self._log_interval != 0 and self.step + 1 < self.n_steps):
             self._pending_centre = True
             return
@@ -605,6 +659,14 @@ class ES:
     def _hooks_generation(self):
         """The reference's control flow (estorch.py:215-246) through its hooks."""
         policy, optimizer = self._get_policy()
+        if self.n_workers > 1 and self._ALGORITHM_TYPE == _Algorithm.novelty:
+            # only the reference's master selects the meta-policy (estorch.py:444-456)
+            import torch.distributed as dist
+            box = [getattr(self, "idx", 0)]
+            dist.broadcast_object_list(box, src=0)
+            self.idx = int(box[0])
+            self._active = self._slots[self.idx]
+            policy, optimizer = self.meta_population[self.idx]
         self.population_parameters, epsilon = self._sample_policy(policy)
         per = self.population_size // self.n_workers
         pop = self.population_parameters
@@ -643,6 +705,16 @@ class ES:
             index += size
         optimizer.step()                                              # estorch.py:245
         self._after_optimize(policy)
+        if self.n_workers > 1 and self._ALGORITHM_TYPE == _Algorithm.novelty:
+            # the master's post-update rollout is the one that enters the archive and drives
+            # the NSRA schedule (estorch.py:427-432, :458-471 broadcast the archive)
+            import torch.distributed as dist
+            box = [{k: getattr(self, k) for k in ("episode_reward", "best_reward", "weight", "t") if hasattr(self, k)}
+                   | {"bc": self._archive[-1]}]
+            dist.broadcast_object_list(box, src=0)
+            self._archive[-1] = box[0].pop("bc")
+            for k, v in box[0].items():
+                setattr(self, k, v)
 
     # ------------------------------------------------------------------ main loop
     def _master(self):
@@ -652,6 +724,7 @@ class ES:
         self._ensure_dist()
         for s in self._slots:
             s.ensure_flat()
+        self._sync_replicas()
         with torch.no_grad():
             while self.step < self.n_steps and not self._stop:
                 self._gen_token += 1
@@ -790,10 +863,10 @@ class NS_ES(ES):
     def __init__(self, policy, agent, optimizer, population_size, sigma=0.01,
                  meta_population_size=3, k=10, device=torch.device("cpu"),
                  policy_kwargs={}, agent_kwargs={}, optimizer_kwargs={}, **engine_kwargs):
+        self.meta_population_size = meta_population_size
+        self.k = k            # known before _decide_fused(): the device kNN keeps k <= 32 neighbours
         super().__init__(policy, agent, optimizer, population_size, sigma, device,
                          policy_kwargs, agent_kwargs, optimizer_kwargs, **engine_kwargs)
-        self.meta_population_size = meta_population_size
-        self.k = k
         self._archive = []
         self.meta_population = []
         self._ensure_novelty()
@@ -816,6 +889,7 @@ class NS_ES(ES):
         self._active = self._slots[0]
         self._best_host = -float("inf")
 
+    @_builtin
     def _rollout_bc(self, policy):
         """Initial archive entry of a meta-population member (estorch.py:405)."""
         if self._fused:

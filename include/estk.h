@@ -93,7 +93,9 @@ ESTK_API int estk_ctx_info(estk_ctx* ctx, int* sm_count, int* cc_major, int* cc_
  *      Normal(0,sigma).sample per generation) ---- */
 
 /* Fill table[0:len) with unit normals: Philox4x32-10(counter=i/4, key=seed)
- * + Box-Muller.  len % 4 == 0.  Identical on every GPU for the same seed. */
+ * + Box-Muller, each entry then rounded to the nearest fp16-representable value
+ * (11 significant bits; still stored as fp32 here) so that the 16-bit copy made by
+ * estk_shadow_f16 is exact.  len % 4 == 0.  Identical on every GPU for the same seed. */
 ESTK_API int estk_fill_noise_table(estk_ctx* ctx, float* table, int64_t len, uint64_t seed,
                           void* stream);
 
@@ -130,7 +132,7 @@ ESTK_API int estk_eval_mlp(estk_ctx* ctx, const estk_mlp_desc* desc, const float
                   float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim,
                   void* stream);
 
-/* Tensor-core variant of estk_eval_mlp: same contract, bf16 operands with fp32
+/* Opt-in lower-precision tensor-core variant of estk_eval_mlp: same contract, bf16 operands with fp32
  * accumulation on tcgen05 (weights theta+-sigma*eps are rounded to bf16 when the
  * B-operand tile is formed, activations when they are written back).  Shapes:
  * every layer input width a multiple of 64 in [64,512], every output width a
@@ -152,7 +154,36 @@ ESTK_API int estk_eval_mlp_center_bf16(estk_ctx* ctx, const estk_mlp_desc* desc,
                               void* stream);
 ESTK_API int estk_eval_mlp_bf16_supported(const estk_mlp_desc* desc, int32_t B);
 
-/* "bf16s": as estk_eval_mlp_bf16, but the weight producers read bf16 SHADOWS of
+/* DEFAULT tensor-core evaluate ("f16"): same contract as estk_eval_mlp, computed on
+ * tcgen05 with fp16 operands (11-bit significand, the TF32 class) and fp32 accumulation.
+ * Every weight is formed in fp32 from the fp32 theta and the noise value and rounded ONCE:
+ *   W16 = rn_f16(theta + s*sigma*T[off+i])      (sum in fp32, like estorch.py:192)
+ * The noise is streamed from table16, a 16-bit copy of `table` that must be EXACT
+ * (table16[i] == table[i] for all i: build it with estk_shadow_f16, whose inexact_count
+ * must come back 0 -- true for tables made by estk_fill_noise_table); the kernel
+ * therefore evaluates exactly the members the gradient estimate (estk_rank_grad*, fp32
+ * table) weights.  Hidden activations are rounded to fp16 when written back (saturating
+ * at +-65504), the observations enter as x_hi + x_lo (two fp16 operands), biases and the
+ * squared error are fp32.  Shapes as estk_eval_mlp_bf16, plus dims[0] <= 256
+ * (estk_eval_mlp_f16_supported()).  Measured agreement with the fp32 path: see
+ * tests/test_kernels_gpu.py::test_eval_mlp_f16_* and profiles/. */
+ESTK_API int estk_shadow_f16(estk_ctx* ctx, const float* src, uint16_t* dst, int64_t n,
+                    uint64_t* inexact_count /* device, nullable: += #entries that changed */,
+                    void* stream);
+ESTK_API int estk_eval_mlp_f16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                      const float* table, const uint16_t* table16,
+                      const int64_t* offsets, const int32_t* order, int32_t pairs, float sigma,
+                      const float* obs, const float* target, int32_t B,
+                      float* returns_plus, float* returns_minus,
+                      float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim,
+                      float* centre_return_out, void* stream);
+ESTK_API int estk_eval_mlp_center_f16(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta,
+                             const float* obs, const float* target, int32_t B,
+                             float* return_out, float* bc_out, int32_t bc_obs, int32_t bc_dim,
+                             void* stream);
+ESTK_API int estk_eval_mlp_f16_supported(const estk_mlp_desc* desc, int32_t B);
+
+/* "bf16s" (opt-in, lower precision): as estk_eval_mlp_bf16, but the weight producers read bf16 SHADOWS of
  * theta and of the noise table (theta16[i] = bf16(theta[i]), table16[i] =
  * bf16(table[i]), built with estk_shadow_bf16) -- half the bytes per weight
  * element, W = bf16(theta16 + s*sigma*table16[off+i]).  Biases still come from the

@@ -32,6 +32,7 @@ __all__ = [
     "compute_ranks", "center_values", "rank_transformation",
     "mix64", "noise_slots", "noise_offsets", "philox4x32_10", "philox_normal_table",
     "mlp_param_count", "mlp_unflatten", "mlp_forward", "mlp_forward_bf16", "round_bf16", "synthetic_return", "synthetic_bc",
+    "round_f16", "mlp_forward_f16",
     "sample_population", "sample_population_bf16s", "evaluate_population",
     "blend_weights", "calculate_grad", "calculate_grad_pairs", "negate_clamp",
     "adam_step", "novelty", "nsra_weight_update", "vbn_stats", "vbn_normalize",
@@ -151,7 +152,9 @@ def philox_normal_table(length: int, seed: int) -> np.ndarray:
         ang = (two_pi * us[2 * h + 1]).astype(np.float32)
         out[:, 2 * h] = r * np.cos(ang).astype(np.float32)
         out[:, 2 * h + 1] = r * np.sin(ang).astype(np.float32)
-    return out.reshape(-1)
+    # estk_fill_noise_table rounds every entry to the nearest fp16-representable value
+    # (round-to-nearest-even, like numpy's float32 -> float16), so a 16-bit copy is exact
+    return out.reshape(-1).astype(np.float16).astype(np.float32)
 
 
 # --------------------------------------------------------------------------
@@ -208,6 +211,28 @@ def mlp_forward_bf16(flat: np.ndarray, dims: Sequence[int], obs: np.ndarray) -> 
         else:
             h = z.astype(np.float32)
     return h
+
+
+def round_f16(x: np.ndarray) -> np.ndarray:
+    """fp32 -> nearest fp16 (ties to even, saturating at +-65504) -> fp32: the operand
+    rounding of the fp16 tensor-core evaluate (cvt.rn.satfinite.f16x2.f32)."""
+    return np.clip(np.asarray(x, dtype=np.float32), -65504.0, 65504.0).astype(np.float16).astype(np.float32)
+
+
+def mlp_forward_f16(flat: np.ndarray, dims: Sequence[int], obs: np.ndarray) -> np.ndarray:
+    """Emulation of estk_eval_mlp_f16's roundings (test infrastructure for the kernel's
+    own arithmetic; parity proper is against mlp_forward): weights and hidden activations
+    rounded to fp16, the observation split x_hi + x_lo, fp32 (here fp64) accumulation,
+    fp32 bias."""
+    x = np.asarray(obs, dtype=np.float32)
+    x_hi = round_f16(x)
+    h = x_hi.astype(np.float64) + round_f16(x - x_hi).astype(np.float64)
+    layers = mlp_unflatten(np.asarray(flat, dtype=np.float32), dims)
+    for i, (w, b) in enumerate(layers):
+        h = (h @ round_f16(w).astype(np.float64).T + b.astype(np.float64)).astype(np.float32)
+        if i + 1 < len(layers):
+            h = round_f16(np.maximum(h, 0.0)).astype(np.float64)
+    return h.astype(np.float32)
 
 
 def synthetic_return(out: np.ndarray, target: np.ndarray) -> np.float32:

@@ -31,6 +31,15 @@ class OracleBackend:
             all(n % 32 == 0 and 32 <= n <= 512 for n in dims[1:]) and B % 256 == 0
         return bool(self.tensor_core and ok)
 
+    def eval_supports_f16(self, dims, B):
+        return self.eval_supports_bf16(dims, B) and 2 * dims[0] <= 512
+
+    def shadow_f16(self, src, dst, check=True):
+        a = _np(src)
+        h = a.astype(np.float16)
+        dst.copy_(torch.from_numpy(h))
+        return int(np.count_nonzero(h.astype(np.float32) != a)) if check else 0
+
     def shadow_bf16(self, src, dst):
         dst.copy_(torch.from_numpy(orc.round_bf16(_np(src))).to(torch.bfloat16))
 
@@ -73,13 +82,17 @@ class OracleBackend:
             eps_out.copy_(torch.from_numpy(eps[sl]))
 
     def eval_mlp(self, dims, theta, table, offsets, order, pairs, sigma, obs, target, ret_plus, ret_minus,
-                 bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32", centre_out=None, **_):
+                 bc_plus=None, bc_minus=None, bc_obs=0, bc_dim=0, precision="fp32", centre_out=None, **extra):
         pop, _ = orc.sample_population(_np(theta), _np(table), _np(offsets), sigma)
-        if precision in ("bf16", "bf16s"):
+        if precision in ("f16", "bf16", "bf16s"):
             assert self.tensor_core and bc_plus is None
-            rows = pop.copy() if precision == "bf16" else self._exact_biases(
+            if precision == "f16":
+                t16 = extra["table16"]
+                assert t16.dtype == torch.float16 and np.array_equal(_np(t16).astype(np.float32), _np(table))
+            rows = pop.copy() if precision != "bf16s" else self._exact_biases(
                 orc.sample_population_bf16s(_np(theta), _np(table), _np(offsets), sigma), pop, list(dims))
-            rets = np.array([orc.synthetic_return(orc.mlp_forward_bf16(r, list(dims), _np(obs)), _np(target))
+            fwd = orc.mlp_forward_f16 if precision == "f16" else orc.mlp_forward_bf16
+            rets = np.array([orc.synthetic_return(fwd(r, list(dims), _np(obs)), _np(target))
                              for r in rows], dtype=np.float32)
             ret_plus.copy_(torch.from_numpy(rets[:pairs]))
             ret_minus.copy_(torch.from_numpy(rets[pairs:]))
@@ -97,7 +110,9 @@ class OracleBackend:
 
     def eval_mlp_center(self, dims, theta, obs, target, ret_out, bc_out=None, bc_obs=0, bc_dim=0, precision="fp32", **_):
         th = _np(theta)
-        if precision in ("bf16", "bf16s"):
+        if precision == "f16":
+            out = orc.mlp_forward_f16(th, list(dims), _np(obs))
+        elif precision in ("bf16", "bf16s"):
             row = th if precision == "bf16" else self._exact_biases(orc.round_bf16(th).copy(), th, list(dims))
             out = orc.mlp_forward_bf16(row, list(dims), _np(obs))
         else:

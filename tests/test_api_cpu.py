@@ -376,8 +376,8 @@ def test_checkpoint_resume_hooks_mode(tmp_path):
 
 
 # ------------------------------------------------------------------ folded post-update rollout (host logic)
-def _tc_es(log_interval, seen=None, n=16):
-    """Fused ES on the emulated tensor-core backend (bf16s): the only mode that folds."""
+def _tc_es(log_interval, seen=None, n=16, precision="auto"):
+    """Fused ES on the emulated tensor-core backend (the modes that fold the post-update rollout)."""
     dims = [64, 64, 32]
     g = torch.Generator().manual_seed(2)
     obs, tgt = torch.randn(256, 64, generator=g), torch.randn(256, 32, generator=g)
@@ -390,19 +390,20 @@ def _tc_es(log_interval, seen=None, n=16):
     be = OracleBackend(tensor_core=True)
     es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=n, sigma=0.02, policy_kwargs={"dims": dims},
            agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 14,
-           log_interval=log_interval, _backend=be)
-    assert es._fused and es._precision == "bf16s"
+           log_interval=log_interval, eval_precision=precision, _backend=be)
+    assert es._fused and es._precision == ("f16" if precision == "auto" else precision)
     return es, be
 
 
-def test_deferred_post_update_rollout_is_equivalent_cpu():
+@pytest.mark.parametrize("precision", ["auto", "bf16s"])
+def test_deferred_post_update_rollout_is_equivalent_cpu(precision):
     """estorch.py:181-185 runs one rollout of the updated policy per generation.  With
     log_interval > 1 that rollout is folded into the next generation's evaluate launch;
     everything observable must equal the log_interval = 1 run."""
     out = {}
     for li in (1, 3):
         seen = []
-        es, be = _tc_es(li, seen)
+        es, be = _tc_es(li, seen, precision=precision)
         es.train(n_steps=7)
         out[li] = dict(theta=es._slots[0].theta.clone(), best=es._slots[0].best_theta.clone(), seen=seen,
                        ep=es.episode_reward, br=es.best_reward, ret=es.population_returns.copy(), folds=be.centre_folds)

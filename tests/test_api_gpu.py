@@ -125,7 +125,7 @@ def test_ns_family_fused_vs_reference_golden(algo, cls):
     assert rel_err(final, g["meta_theta_final"]) < 5e-3
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-3), ("bf16s", 1e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("auto", 1e-5), ("bf16", 1e-3), ("bf16s", 1e-3)])
 def test_north_star_shape_one_generation_properties(precision, tol):
     """BASELINE north-star sizes (P=4096, n=1,001,760, B=256): one fused generation;
     ranks are a permutation, theta moved by ~lr everywhere, returns finite/unique."""
@@ -140,7 +140,7 @@ def test_north_star_shape_one_generation_properties(precision, tol):
     es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=4096, sigma=0.02,
            policy_kwargs={"dims": dims}, agent_kwargs=dict(obs=obs, target=tgt),
            optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 26, eval_precision=precision)
-    assert es.n_parameters == 1001760 and es._fused and es._precision == precision
+    assert es.n_parameters == 1001760 and es._fused and es._precision == ("f16" if precision == "auto" else precision)
     before = es._slots[0].theta.clone()
     es.train(n_steps=1)
     ret = es.population_returns[:, 0]
@@ -242,7 +242,7 @@ def test_deferred_post_update_rollout_is_equivalent():
         es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=128, sigma=0.02, policy_kwargs={"dims": dims},
                agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22,
                log_interval=li)
-        assert es._precision == "bf16s"
+        assert es._precision == "f16"
         es.train(n_steps=7)
         out[li] = dict(theta=es._slots[0].theta.clone(), best=es._slots[0].best_theta.clone(), seen=seen,
                        ep=es.episode_reward, br=es.best_reward, ret=es.population_returns.copy())

@@ -6,7 +6,7 @@ be = CudaBackend(torch.device("cuda", 0))
 dims = [128, 512, 512, 512, 512, 288]
 n = sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1))
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-mode = sys.argv[2] if len(sys.argv) > 2 else "bf16s"
+mode = sys.argv[2] if len(sys.argv) > 2 else "f16"
 table = be.alloc(1 << 28); be.fill_noise_table(table, 42)
 offs = be.alloc(pairs, dtype=torch.int64); order = be.alloc(pairs, dtype=torch.int32)
 be.make_offsets(42, None, 0, 0, pairs, table.numel(), n, offs, order)
@@ -14,10 +14,15 @@ torch.manual_seed(0)
 theta = torch.randn(n, device=be.device) * 0.05
 obs, tgt = torch.randn(256, 128, device=be.device), torch.randn(256, 288, device=be.device)
 ret = be.zeros(2 * pairs)
-th16 = be.alloc(n, dtype=torch.bfloat16); tb16 = be.alloc(table.numel(), dtype=torch.bfloat16)
-be.shadow_bf16(theta, th16); be.shadow_bf16(table, tb16)
+th16 = be.alloc(n, dtype=torch.bfloat16)
+if mode == "f16":
+    tb16 = be.alloc(table.numel(), dtype=torch.float16); assert be.shadow_f16(table, tb16) == 0
+else:
+    tb16 = be.alloc(table.numel(), dtype=torch.bfloat16); be.shadow_bf16(table, tb16)
+be.shadow_bf16(theta, th16)
+kw = {"table16": tb16} if mode == "f16" else {"theta16": th16, "table16": tb16} if mode == "bf16s" else {}
 run = lambda: be.eval_mlp(dims, theta, table, offs, order, pairs, 0.02, obs, tgt, ret[:pairs], ret[pairs:],
-                          precision=mode, theta16=th16, table16=tb16)
+                          precision=mode, **kw)
 for _ in range(3):
     run()
 torch.cuda.synchronize()

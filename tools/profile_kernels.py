@@ -20,12 +20,11 @@ be.make_offsets(42, None, 0, 0, pairs, table.numel(), n, offs, order)
 theta, m, v = torch.randn(n, device=be.device) * 0.05, be.zeros(n), be.zeros(n)
 obs, tgt = torch.randn(B, dims[0], device=be.device), torch.randn(B, dims[-1], device=be.device)
 ret = be.zeros(P); st = new_state(be.device); ranks = be.zeros(P, dtype=torch.int32)
-th16 = be.alloc(n, dtype=torch.bfloat16); tb16 = be.alloc(table.numel(), dtype=torch.bfloat16)
-be.shadow_bf16(theta, th16); be.shadow_bf16(table, tb16)
+tb16 = be.alloc(table.numel(), dtype=torch.float16); assert be.shadow_f16(table, tb16) == 0
 for _ in range(a.iters):
     if a.what in ("both", "eval"):
-        be.eval_mlp(dims, theta, table, offs, order, pairs, 0.02, obs, tgt, ret[:pairs], ret[pairs:], precision="bf16s",
-                    theta16=th16, table16=tb16)
+        be.eval_mlp(dims, theta, table, offs, order, pairs, 0.02, obs, tgt, ret[:pairs], ret[pairs:], precision="f16",
+                    table16=tb16)
     if a.what in ("both", "grad"):
         be.rank_grad_adam(ret, None, 1.0, 0.0, P, table, offs, order, theta, m, v, st, adam_desc(lr=0.01), ranks, None, None)
 torch.cuda.synchronize()

@@ -17,12 +17,15 @@ ret = be.zeros(2 * pairs)
 buf = (ctypes.c_ulonglong * 32)()
 names = ["mma.total", "mma.wait_h", "mma.wait_full", "mma.issue", "prod.total", "prod.setup", "prod.stages", "prod.wait_empty",
          "prod.load+form+store", "prod.fence+arrive", "epi.total", "epi.obs", "epi.bias+bar+arrive", "epi.wait_acc", "epi.tmem+process", "epi.tmem_ld+wait"]
-mode = os.environ.get("TC_MODE", "bf16s")
-th16 = be.alloc(n, dtype=torch.bfloat16); tb16 = be.alloc(table.numel(), dtype=torch.bfloat16)
-be.shadow_bf16(theta, th16); be.shadow_bf16(table, tb16)
+mode = os.environ.get("TC_MODE", "f16")
+th16 = be.alloc(n, dtype=torch.bfloat16); be.shadow_bf16(theta, th16)
+if mode == "f16":
+    tb16 = be.alloc(table.numel(), dtype=torch.float16); assert be.shadow_f16(table, tb16) == 0
+else:
+    tb16 = be.alloc(table.numel(), dtype=torch.bfloat16); be.shadow_bf16(table, tb16)
+kw = {"table16": tb16} if mode == "f16" else {"theta16": th16, "table16": tb16} if mode == "bf16s" else {}
 for rep in range(2):
-    be.eval_mlp(dims, theta, table, offs, order, pairs, 0.02, obs, tgt, ret[:pairs], ret[pairs:], precision=mode,
-                theta16=th16, table16=tb16)
+    be.eval_mlp(dims, theta, table, offs, order, pairs, 0.02, obs, tgt, ret[:pairs], ret[pairs:], precision=mode, **kw)
     lib.estk_debug_tc_profile(buf, 32)
 tasks = -(-pairs * 2 // 74)
 print(f"pairs={pairs} tasks/cluster~{tasks}")
