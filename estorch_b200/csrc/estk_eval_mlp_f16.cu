@@ -1,0 +1,664 @@
+// estk_eval_mlp_f16.cu -- kernel 1 of the ES generation (population evaluate) on the 5th-gen
+// tensor cores, fp16 operands / fp32 accumulation, warpgroup-specialised.
+//
+// Contract: estk_eval_mlp_f16 in include/estk.h (reference estorch.py:187-202 `_sample_policy` +
+// `_calculate_returns`, Policy.forward examples/cartpole_es.py:14-20, synthetic agent SURVEY 8d).
+//
+// Arithmetic.  Per member W_s = theta + s*sigma*eps is formed in fp32 from the fp32 theta and the
+// noise value (streamed from the EXACT 16-bit copy of the table) and rounded ONCE to fp16 (11-bit
+// significand, the TF32 class); hidden activations are rounded to fp16 when they are written back
+// (bias + ReLU in fp32 first); the observations enter layer 0 as x_hi + x_lo (two fp16 operands on
+// the same weight tile); accumulation, bias, squared error in fp32.
+//
+// Work unit ("task") = (antithetic pair j, sign s, chunk of 256 observations) on a cluster of two
+// CTAs, tcgen05.mma.cta_group::2, UMMA M = 256 (128 observation rows per CTA).  Per layer
+//   D[obs, out] = H[obs, in] * W_s[out, in]^T
+//   A  activations H: 128 rows per CTA, fp16, K-major, 128B-swizzled, RESIDENT in shared memory
+//      across layers (8 k-blocks x 16 KB, updated in place);
+//   B  W_s formed ON THE FLY into a 5-stage ring of [128 x 64] tiles (each CTA forms its half of
+//      the N tile) -- the perturbed weights never exist in global memory;
+//   D  the whole layer output [128 x <=512] fp32 in TMEM (512 columns) as two N tiles.
+// Warp roles (20 warps, homogeneous warpgroups so that setmaxnreg can move registers):
+//   WG0    w0 MMA issuer (leader CTA), w1 TMEM allocator, w2-3 idle           -> 40 registers
+//   WG1-2  8 epilogue warps: two per TMEM lane quarter, each half of the columns -> 112
+//   WG3-4  8 weight producers in 2 groups of 4 warps (rolling 4-item load window)  -> 104
+// Epilogue schedule per layer: tile 0 is drained while tile 1's MMAs still run (they read the
+// activations, which therefore cannot be overwritten yet) -- bias, ReLU, fp16, parked as packed
+// pairs in the TMEM columns the drain itself freed; when the layer is accumulated the parked half
+// moves to smem (k-blocks 0..3, hand-over 0) and tile 1 is drained straight into k-blocks 4..7
+// (hand-over 1) under the next layer's first MMAs.  One mbarrier per hand-over index (a shared one
+// can alias phases, profiles/README.md).  The last layer is fused with the squared error.
+//
+// Roofline: 2*n*B*2*pairs flops per launch on the tensor pipe; L2 -> SM ingest 6 B per weight
+// element and sign (fp32 theta + fp16 noise); the noise stream 2*n*pairs bytes is read once from
+// HBM (the second sign of a pair runs on the neighbouring cluster at the same time: L2 hit).
+#include "estk_tc.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef ESTK_TC_PROFILE
+__device__ unsigned long long g_f16_prof[32];   // per-role cycle counters of CTA 0 (triage builds only)
+#define PROF_T() (prof ? clock64() : 0ll)
+#define PROF_ADD(i, t0) do { if (prof) atomicAdd(&g_f16_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define PROF_T() 0ll
+#define PROF_ADD(i, t0) do { (void)(t0); } while (0)
+#endif
+
+namespace {
+
+constexpr int CG = 2;                         // CTAs per cluster = tcgen05 cta_group
+constexpr int kStages = 5;                    // B ring depth (16 KB stages beside 128 KB of activations)
+constexpr int kStageBytes = kKBlockBytes;
+constexpr int kCtlWarps = 4, kEpiWarps = 8, kProdWarps = 8;
+constexpr int kEpiWarp0 = kCtlWarps, kProdWarp0 = kCtlWarps + kEpiWarps;
+constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, launched at 96 registers
+#ifndef ESTK_F16_GROUPS
+#define ESTK_F16_GROUPS 2
+#endif
+constexpr int kProdGroups = ESTK_F16_GROUPS, kProdGroupWarps = kProdWarps / kProdGroups, kPT = 32 * kProdGroupWarps;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+// 128*40 + 256*112 + 256*104 = 60416 <= 640*96 = 61440
+constexpr int kRegsCtl = 40, kRegsEpi = 112, kRegsProd = 104;
+
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+struct EvalF16Params {
+  estk_mlp_desc desc;
+  const float* theta;
+  const float* table;        // fp32 table (biases); == theta for the centre-only launch
+  const uint16_t* table16;   // exact fp16 copy of the table (weights); null for the centre-only launch
+  const int64_t* offsets;    // null => centre evaluation
+  const int32_t* order;
+  int pairs;
+  float sigma;
+  const float* obs;
+  const float* target;
+  int B, chunks;             // chunks of 128*CG observations
+  float* ret_plus;
+  float* ret_minus;
+  float* bc_plus;
+  float* bc_minus;
+  int bc_obs, bc_dim;
+  float* partial;            // [pairs*2 + 1][chunks*CG]
+  unsigned int* counters;    // [pairs*2 + 1]
+  float* centre_out;         // optional: also evaluate theta itself (sigma = 0) into centre_out[0]
+  int n_centre;              // number of leading centre tasks (0 or chunks)
+  int n_tasks;               // n_centre + pairs * n_signs * chunks
+  int n_signs;               // 2, or 1 for the centre evaluation
+  int prof;
+};
+
+struct Layer { int K, N; int64_t wbase, bbase; };
+
+// task -> (slot, sign, chunk); the first n_centre tasks evaluate theta itself
+struct TaskId { int slot, sgn, chunk; bool centre; };
+__device__ __forceinline__ TaskId decode_task(const EvalF16Params& p, int task, bool all_centre) {
+  TaskId t;
+  if (task < p.n_centre) { t.slot = 0; t.sgn = 0; t.chunk = task; t.centre = true; return t; }
+  const int q = task - p.n_centre;
+  t.chunk = q % p.chunks;
+  t.sgn = (q / p.chunks) % p.n_signs;
+  t.slot = q / (p.chunks * p.n_signs);
+  t.centre = all_centre;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sH = smem;                                    // 8 k-blocks x 16 KB
+  uint8_t* sB = sH + (kMaxW / kBlockK) * kKBlockBytes;   // ring
+  float* sBias = reinterpret_cast<float*>(sB + kStages * kStageBytes);   // [2][512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * kMaxW);
+  uint64_t* bar_full = bars;                   // [kStages]  weights of the stage formed        (leader's are used)
+  uint64_t* bar_empty = bars + kStages;        // [kStages]  stage consumed by the MMAs          (local)
+  uint64_t* bar_acc0 = bars + 2 * kStages;     // first N tile of a two-tile layer accumulated   (local)
+  uint64_t* bar_acc = bars + 2 * kStages + 1;  // layer accumulated                              (local)
+  uint64_t* bar_h = bars + 2 * kStages + 2;    // [2] next layer's k-blocks 0..3 / 4..7 in place (leader's are used)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kEpiWarps]
+  __shared__ Layer lay[ESTK_MAX_LAYERS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / CG, n_clusters = gridDim.x / CG;
+  const int L = p.desc.n_layers;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(bar_full + s), CG * kProdGroupWarps);
+      mbar_init(smem_u32(bar_empty + s), 1);
+    }
+    mbar_init(smem_u32(bar_acc0), 1);
+    mbar_init(smem_u32(bar_acc), 1);
+    mbar_init(smem_u32(bar_h + 0), CG * kEpiWarps);
+    mbar_init(smem_u32(bar_h + 1), CG * kEpiWarps);
+    fence_barrier_init();
+  }
+  if (threadIdx.x == 32) {          // per-layer geometry, in shared memory
+    int64_t pb = 0;
+    for (int l = 0; l < L; ++l) {
+      lay[l].K = p.desc.dims[l];
+      lay[l].N = p.desc.dims[l + 1];
+      lay[l].wbase = pb;
+      lay[l].bbase = pb + (int64_t)lay[l].K * lay[l].N;
+      pb = lay[l].bbase + lay[l].N;
+    }
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc<CG>(smem_u32(s_tmem), 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+  const bool centre = (p.offsets == nullptr);
+#ifdef ESTK_TC_PROFILE
+  const bool prof = p.prof && blockIdx.x == 0 && lane == 0;
+#endif
+
+  if (warp < kCtlWarps) {
+    setmaxnreg_dec<kRegsCtl>();
+    if (warp == 0 && cta_rank == 0) {
+      // =================================================================== MMA issuer
+      uint32_t stage = 0, ring_phase = 0, h_phase0 = 0, h_phase1 = 0;
+      const long long tm0 = PROF_T();
+      for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
+        for (int l = 0; l < L; ++l) {
+          const long long th0 = PROF_T();
+          mbar_wait(smem_u32(bar_h + 0), h_phase0);     // k-blocks 0..3 of this layer's input are in place,
+          h_phase0 ^= 1;                                // TMEM columns [0,256) are drained
+          PROF_ADD(1, th0);
+          tc_fence_after();
+          const int K = lay[l].K, N = lay[l].N;
+          bool second_half_ready = (K <= 256) || (l == 0);   // hidden inputs wider than 256 arrive in two halves
+          const int lo_kb = (l == 0) ? K / kBlockK : 0;      // layer 0: x_lo lives K/64 k-blocks after x_hi
+          for (int n0 = 0; n0 < N; n0 += 256) {
+            const int Ng = min(256, N - n0);
+            const uint32_t idesc = make_idesc(128 * CG, Ng, true);
+            const uint32_t tmem_d = tmem_base + (uint32_t)n0;
+            for (int kb = 0; kb < K / kBlockK; ++kb) {
+              if (kb >= 4 && !second_half_ready) {   // k-blocks 4..7 in place, TMEM columns [256,512) drained
+                const long long th1 = PROF_T();
+                mbar_wait(smem_u32(bar_h + 1), h_phase1);
+                h_phase1 ^= 1;
+                PROF_ADD(1, th1);
+                tc_fence_after();
+                second_half_ready = true;
+              }
+              const long long tf0 = PROF_T();
+              mbar_wait(smem_u32(bar_full + stage), ring_phase);
+              PROF_ADD(2, tf0);
+              const long long ti0 = PROF_T();
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a_addr = smem_u32(sH + kb * kKBlockBytes);
+                const uint32_t b_addr = smem_u32(sB + stage * kStageBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16<CG>(tmem_d, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
+                if (lo_kb) {
+                  const uint32_t a_lo = smem_u32(sH + (kb + lo_kb) * kKBlockBytes);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_bf16<CG>(tmem_d, make_sw128_desc(a_lo + k * 32), make_sw128_desc(b_addr + k * 32), idesc, 1u);
+                }
+                umma_commit<CG>(smem_u32(bar_empty + stage));          // frees the ring slot (both CTAs)
+                if (kb + 1 == K / kBlockK) {
+                  if (n0 + 256 >= N) umma_commit<CG>(smem_u32(bar_acc));     // layer accumulated
+                  else umma_commit<CG>(smem_u32(bar_acc0));                  // tile 0 of 2: its drain overlaps tile 1's MMAs
+                }
+              }
+              __syncwarp();
+              PROF_ADD(3, ti0);
+              if (++stage == kStages) { stage = 0; ring_phase ^= 1; }
+            }
+          }
+        }
+      }
+      PROF_ADD(0, tm0);
+    }
+  } else if (warp < kProdWarp0) {
+    // =================================================================== epilogue warps
+    setmaxnreg_inc<kRegsEpi>();
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                  // which half of the columns of a tile this warp drains
+    const int row = q * 32 + lane;             // observation row inside the CTA's 128
+    const int etid = ew * 32 + lane;           // 0..255
+    uint32_t acc_phase = 0, acc0_phase = 0;
+#ifdef ESTK_TC_PROFILE
+    const bool eprof = prof && ew == 0;
+#define EPROF_T() (eprof ? clock64() : 0ll)
+#define EPROF_ADD(i, t0) do { if (eprof) atomicAdd(&g_f16_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define EPROF_T() 0ll
+#define EPROF_ADD(i, t0) do { (void)(t0); } while (0)
+#endif
+    const long long te0 = EPROF_T();
+    const uint32_t trow_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    // next layer's input is handed over per k-block half: index 0 = k-blocks 0..3, 1 = 4..7
+    auto hand_over = [&](int idx) {
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h + idx), 0);
+    };
+    for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
+      const long long to0 = EPROF_T();
+      const TaskId tk = decode_task(p, task, centre);
+      const int chunk = tk.chunk, sgn = tk.sgn, slot = tk.slot;
+      const int j = (!tk.centre && p.order) ? p.order[slot] : slot;
+      const float* trow = tk.centre ? p.theta : p.table + p.offsets[j];
+      const float ssig = tk.centre ? 0.f : (sgn ? -p.sigma : p.sigma);
+      const int b = (chunk * CG + (int)cta_rank) * 128 + row;      // global observation index
+      // ---- stage this CTA's observations as the layer-0 A operand: x = x_hi + x_lo (fp16 each);
+      //      the two warps of a lane quarter split the 16-byte chunks of a row
+      {
+        const int K0 = lay[0].K;
+        const float* orow = p.obs + (size_t)b * K0;
+        const int cper = K0 / 16;                                  // 8-element chunks per warp (K0/8 in total)
+        for (int cc = 0; cc < cper; cc += 4) {
+          float4 x[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (cc + u < cper) {
+              const int c = half * cper + cc + u;
+              x[u][0] = __ldg(reinterpret_cast<const float4*>(orow + c * 8));
+              x[u][1] = __ldg(reinterpret_cast<const float4*>(orow + c * 8 + 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (cc + u < cper) {
+              const int c = half * cper + cc + u;
+              const uint32_t off = sw128_offset(row, c & 7);
+              const uint32_t h0 = pack_f16(x[u][0].x, x[u][0].y), h1 = pack_f16(x[u][0].z, x[u][0].w);
+              const uint32_t h2 = pack_f16(x[u][1].x, x[u][1].y), h3 = pack_f16(x[u][1].z, x[u][1].w);
+              st_shared_v4(smem_u32(sH + (c >> 3) * kKBlockBytes) + off, h0, h1, h2, h3);
+              const float2 f0 = unpack_f16(h0), f1 = unpack_f16(h1), f2 = unpack_f16(h2), f3 = unpack_f16(h3);
+              st_shared_v4(smem_u32(sH + ((c >> 3) + K0 / kBlockK) * kKBlockBytes) + off,
+                           pack_f16(x[u][0].x - f0.x, x[u][0].y - f0.y), pack_f16(x[u][0].z - f1.x, x[u][0].w - f1.y),
+                           pack_f16(x[u][1].x - f2.x, x[u][1].y - f2.y), pack_f16(x[u][1].z - f3.x, x[u][1].w - f3.y));
+            }
+          }
+        }
+      }
+      EPROF_ADD(11, to0);
+      // the staged observations are this task's layer-0 input (the previous task's TMEM reads are
+      // long done): release the MMA warp before anything else
+      hand_over(0);
+      float loss = 0.f;
+      for (int l = 0; l < L; ++l) {
+        const long long tb0 = EPROF_T();
+        const int N = lay[l].N;
+        float* bias = sBias + (l & 1) * kMaxW;
+        for (int o = etid; o < N; o += kEpiThreads)
+          bias[o] = fmaf(ssig, ld_noise1(trow + lay[l].bbase + o), __ldg(p.theta + lay[l].bbase + o));
+        named_bar_sync(1, kEpiThreads);   // publishes bias[] among the epilogue warps
+        EPROF_ADD(12, tb0);
+        const bool last = (l == L - 1);
+        const bool two = N > 256;               // two N tiles: columns [0,256) and [256,N)
+        // bias + ReLU + round to fp16: 32 accumulator columns -> 16 packed words
+        auto pack = [&](const uint32_t (&v)[32], int c0, uint32_t (&pk)[16]) {
+          const uint32_t baddr = smem_u32(bias + c0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = ld_shared_v4(baddr + g * 16);
+            pk[g * 2 + 0] = pack_f16_relu(__uint_as_float(v[g * 4 + 0]) + t.x, __uint_as_float(v[g * 4 + 1]) + t.y);
+            pk[g * 2 + 1] = pack_f16_relu(__uint_as_float(v[g * 4 + 2]) + t.z, __uint_as_float(v[g * 4 + 3]) + t.w);
+          }
+        };
+        // `words` packed words (2*words output features starting at feature f0) -> activations in smem
+        auto store_h = [&](const uint32_t* pk, int f0, int words) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {          // chunks of 8 output features = 16 bytes of fp16
+            if (g * 4 < words) {
+              const int col = f0 + g * 8;
+              const uint32_t addr = smem_u32(sH + (col >> 6) * kKBlockBytes) + sw128_offset(row, (col & 63) >> 3);
+              st_shared_v4(addr, pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+            }
+          }
+        };
+        // last layer: fused squared error (and the behaviour characterisation)
+        auto loss_chunk = [&](const uint32_t (&v)[32], int c0) {
+          const uint32_t baddr = smem_u32(bias + c0);
+          const float* trg = p.target + (size_t)b * N + c0;
+          float* bc = (tk.centre && !centre) ? nullptr : (sgn ? p.bc_minus : p.bc_plus);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(trg + g * 4));
+            const float4 b4 = ld_shared_v4(baddr + g * 16);
+            const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int o = c0 + g * 4 + e;
+              const float y = __uint_as_float(v[g * 4 + e]) + bv[e];
+              const float d = y - tv[e];
+              loss = fmaf(d, d, loss);
+              if (bc) {
+                const int64_t idx = (int64_t)b * N + o;
+                if (b < p.bc_obs && idx < p.bc_dim) bc[(size_t)j * p.bc_dim + idx] = y;
+              }
+            }
+          }
+        };
+        const int base_h = 128 * half;          // this warp's half of tile 0: accumulator columns [base_h, base_h+128)
+        if (two) {
+          // ---- tile 0 is accumulated while tile 1's MMAs still run (they read the activations in
+          // smem, so those cannot be overwritten yet): drain tile 0 now.  Hidden layers park the
+          // result as packed fp16 pairs in TMEM columns this warp's own drain has already freed
+          // (columns [c0,c0+32) -> [base_h + (c0-base_h)/2, +16), in place).
+          const long long ta0 = EPROF_T();
+          mbar_wait(smem_u32(bar_acc0), acc0_phase);
+          acc0_phase ^= 1;
+          tc_fence_after();
+          EPROF_ADD(13, ta0);
+          const long long tx0 = EPROF_T();
+          for (int c0 = base_h; c0 < base_h + 128; c0 += 32) {
+            uint32_t va[32];
+            tmem_ld32(trow_addr + (uint32_t)c0, va);
+            tmem_ld_wait();
+            if (last) {
+              loss_chunk(va, c0);
+            } else {
+              uint32_t pk[16];
+              pack(va, c0, pk);
+              tmem_st16(trow_addr + (uint32_t)(base_h + ((c0 - base_h) >> 1)), pk);
+            }
+          }
+          if (!last) tmem_st_wait();
+          EPROF_ADD(15, tx0);
+        }
+        // ---- wait for the whole layer: every MMA that reads the activations has completed
+        const long long ta1 = EPROF_T();
+        mbar_wait(smem_u32(bar_acc), acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        EPROF_ADD(13, ta1);
+        const long long tx1 = EPROF_T();
+        if (!last && two) {
+          // parked half -> activation k-blocks (2*half, 2*half+1); hand-over 0 when both halves are in
+          for (int s0 = 0; s0 < 64; s0 += 32) {
+            uint32_t pk[32];
+            tmem_ld32(trow_addr + (uint32_t)(base_h + s0), pk);
+            tmem_ld_wait();
+            store_h(pk, base_h + 2 * s0, 32);
+          }
+          hand_over(0);
+        }
+        {
+          const int lo = two ? 256 : 0;
+          const int cnt = (N - lo) / 32, first = (cnt + 1) / 2;      // the two warps of a lane quarter split the chunks
+          const int i0 = half ? first : 0, i1 = half ? cnt : first;
+          for (int i = i0; i < i1; ++i) {
+            const int c0 = lo + i * 32;
+            uint32_t va[32];
+            tmem_ld32(trow_addr + (uint32_t)c0, va);
+            tmem_ld_wait();
+            if (last) {
+              loss_chunk(va, c0);
+            } else {
+              uint32_t pk[16];
+              pack(va, c0, pk);
+              store_h(pk, c0, 16);
+            }
+          }
+        }
+        if (!last) hand_over(two ? 1 : 0);       // second half (or the only one when N <= 256)
+        EPROF_ADD(14, tx1);
+      }
+      // ---- squared-error partial of this CTA; the last arriver combines them in fixed order
+      loss = warp_sum_f(loss);
+      if (lane == 0) s_loss[ew] = loss;
+      named_bar_sync(2, kEpiThreads);
+      if (etid == 0) {
+        const float tot = ((s_loss[0] + s_loss[1]) + (s_loss[2] + s_loss[3])) + ((s_loss[4] + s_loss[5]) + (s_loss[6] + s_loss[7]));
+        const int parts = p.chunks * CG;
+        const bool folded = tk.centre && !centre;                 // centre task riding in a population launch
+        const int cell = folded ? p.pairs * 2 : slot * 2 + sgn;
+        float* part = p.partial + (size_t)cell * parts;
+        part[chunk * CG + (int)cta_rank] = tot;
+        __threadfence();
+        const unsigned int arrived = atomicAdd(p.counters + cell, 1u);
+        if (arrived == (unsigned int)parts - 1) {
+          __threadfence();
+          float s = 0.f;
+          for (int c = 0; c < parts; ++c) s += __ldcg(part + c);
+          const float r = -(s / ((float)p.B * (float)lay[L - 1].N));
+          if (folded) p.centre_out[0] = r;
+          else if (sgn) p.ret_minus[j] = r;
+          else p.ret_plus[j] = r;
+          p.counters[cell] = 0u;
+        }
+      }
+      named_bar_sync(2, kEpiThreads);   // s_loss reusable
+    }
+    EPROF_ADD(10, te0);
+  } else {
+    // =================================================================== weight producers
+    // kProdGroups groups of warps; group g builds stages g, g+G, g+2G, ... of the flattened
+    // (task, layer, n-tile, k-block) stage sequence.  A thread owns 16-byte output chunks of the
+    // [rows x 64] tile: 8 weights = ONE 256-bit load of theta (fp32, L2 resident; a whole 32-byte
+    // sector per thread) + one 128-bit load of the noise row (fp16), W = rn_f16(theta + s*sigma*eps)
+    // with the sum in fp32, one swizzled 128-bit st.shared.  The loads run as a ROLLING window of
+    // kWin items per thread that continues across stage boundaries (the refill of a register set
+    // is issued right after its item has been converted; the ring-slot wait only gates the stores),
+    // so kWin * 48 bytes per thread are in flight all the time.
+    setmaxnreg_inc<kRegsProd>();
+    const int pwarp = warp - kProdWarp0;
+    const int pgroup = pwarp / kProdGroupWarps;
+    const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // thread index inside the group
+    constexpr int kRS = kPT / 8;             // tile rows covered by one item step of the group
+    constexpr int kIU = 128 / kRS;           // item steps per (full) stage
+    constexpr int kWin = 4;                  // items in flight per thread
+    static_assert(kIU >= kWin, "window larger than a stage");
+    const int r0 = ptid >> 3, c8 = ptid & 7;
+    const uint32_t soff = sw128_offset(r0, c8);               // + u * kRS * 128 for item step u
+    struct St { const float* th; const uint16_t* ep; int k_rs; int rows; float sg; uint32_t sbase, stage, phase; };
+    int cached_task = -1;
+    const uint16_t* cached_trow16 = nullptr;
+    float cached_ssig = 0.f;
+    int task = cluster_id, l = 0, n0 = 0, kb = 0;
+    uint32_t counter = pgroup;                                // global stage index of the position (task,l,n0,kb)
+    auto advance = [&]() -> bool {
+      if (++kb >= lay[l].K / kBlockK) {
+        kb = 0;
+        n0 += 256;
+        if (n0 >= lay[l].N) {
+          n0 = 0;
+          if (++l == L) { l = 0; task += n_clusters; }
+        }
+      }
+      return task < p.n_tasks;
+    };
+    // (noise row, signed sigma) of a task: two dependent global loads -- fetched one task ahead
+    int pf_task = -1;
+    const uint16_t* pf_trow16 = nullptr;
+    float pf_ssig = 0.f;
+    auto fetch_task = [&](int t, const uint16_t*& trow16, float& ssig) {
+      const TaskId tk = decode_task(p, t, centre);
+      const int j = (!tk.centre && p.order) ? p.order[tk.slot] : tk.slot;
+      trow16 = tk.centre ? nullptr : p.table16 + p.offsets[j];
+      ssig = tk.centre ? 0.f : (tk.sgn ? -p.sigma : p.sigma);
+    };
+    auto describe = [&](St& d) {             // descriptor of the stage at the current position
+      if (task != cached_task) {
+        cached_task = task;
+        if (task == pf_task) { cached_trow16 = pf_trow16; cached_ssig = pf_ssig; }
+        else fetch_task(task, cached_trow16, cached_ssig);
+        pf_task = task + n_clusters;         // consumed a whole task later: the loads never stall the pipeline
+        if (pf_task < p.n_tasks) fetch_task(pf_task, pf_trow16, pf_ssig);
+      }
+      const int K = lay[l].K;
+      d.rows = min(256, lay[l].N - n0) / CG;                   // this CTA's share of the B tile
+      const int64_t rbase = lay[l].wbase + (int64_t)(n0 + (int)cta_rank * d.rows + r0) * K + kb * kBlockK + c8 * 8;
+      d.th = p.theta + rbase;
+      d.ep = cached_trow16 ? cached_trow16 + rbase : nullptr;
+      d.k_rs = K * kRS;
+      d.sg = cached_ssig;
+      d.stage = counter % kStages;
+      d.phase = (counter / kStages) & 1u;
+      d.sbase = smem_u32(sB + d.stage * kStageBytes) + soff;
+    };
+    bool has_cur = task < p.n_tasks;
+    for (int sk = 0; sk < pgroup && has_cur; ++sk) has_cur = advance();
+    float T[kWin][8];
+    uint4 E[kWin];
+    auto load_item = [&](const St& d, int u, float (&t)[8], uint4& e) {
+      e = make_uint4(0u, 0u, 0u, 0u);
+      if (u * kRS + r0 < d.rows) {
+        ld_noise8(d.th + (size_t)u * d.k_rs, t);
+        if (d.ep) e = ld_noise4u(reinterpret_cast<const uint4*>(d.ep + (size_t)u * d.k_rs));
+      }
+    };
+    auto form_item = [&](const St& d, int u, const float (&t)[8], const uint4& e) {
+      if (u * kRS + r0 < d.rows) {
+        const float2 e0 = unpack_f16(e.x), e1 = unpack_f16(e.y), e2 = unpack_f16(e.z), e3 = unpack_f16(e.w);
+        const uint32_t w0 = pack_f16(fmaf(d.sg, e0.x, t[0]), fmaf(d.sg, e0.y, t[1]));
+        const uint32_t w1 = pack_f16(fmaf(d.sg, e1.x, t[2]), fmaf(d.sg, e1.y, t[3]));
+        const uint32_t w2 = pack_f16(fmaf(d.sg, e2.x, t[4]), fmaf(d.sg, e2.y, t[5]));
+        const uint32_t w3 = pack_f16(fmaf(d.sg, e3.x, t[6]), fmaf(d.sg, e3.y, t[7]));
+        st_shared_v4(d.sbase + (uint32_t)u * (kRS * 128), w0, w1, w2, w3);
+      }
+    };
+#ifdef ESTK_TC_PROFILE
+    const bool pprof = prof && pwarp == 0;
+#define PPROF_T() (pprof ? clock64() : 0ll)
+#define PPROF_ADD(i, t0) do { if (pprof) atomicAdd(&g_f16_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
+#else
+#define PPROF_T() 0ll
+#define PPROF_ADD(i, t0) do { (void)(t0); } while (0)
+#endif
+    const long long tp0 = PPROF_T();
+    St cur = {}, nxt = {};
+    if (has_cur) {
+      describe(cur);
+#pragma unroll
+      for (int u = 0; u < kWin; ++u) load_item(cur, u, T[u], E[u]);
+    }
+    while (has_cur) {
+      bool has_nxt = true;
+      for (int sk = 0; sk < kProdGroups && has_nxt; ++sk) has_nxt = advance();
+      counter += kProdGroups;
+      if (has_nxt) describe(nxt);
+      const long long tw0 = PPROF_T();
+      mbar_wait(smem_u32(bar_empty + cur.stage), cur.phase ^ 1);     // the slot is free (almost always already)
+      PPROF_ADD(7, tw0);
+      const long long tc0 = PPROF_T();
+#pragma unroll
+      for (int u = 0; u < kIU; ++u) {
+        form_item(cur, u, T[u % kWin], E[u % kWin]);
+        if (u + kWin < kIU) load_item(cur, u + kWin, T[u % kWin], E[u % kWin]);
+        else if (has_nxt) load_item(nxt, u + kWin - kIU, T[u % kWin], E[u % kWin]);
+      }
+      PPROF_ADD(8, tc0);
+      const long long tf0 = PPROF_T();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_full + cur.stage), 0);
+      PPROF_ADD(9, tf0);
+      cur = nxt;
+      has_cur = has_nxt;
+    }
+    PPROF_ADD(4, tp0);
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+size_t f16_smem_bytes() {
+  return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)kStages * kStageBytes + 2 * kMaxW * sizeof(float) +
+         (2 * kStages + 4) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + kEpiWarps * sizeof(float) + 64;
+}
+
+int f16_supported(const estk_mlp_desc& d, int B, const char** why) {
+  if (d.n_layers < 1 || d.n_layers > ESTK_MAX_LAYERS) { *why = "n_layers"; return 0; }
+  if (d.activation != 0) { *why = "activation"; return 0; }
+  if (2 * d.dims[0] > kMaxW) { *why = "the observations enter as hi + lo halves: input width <= 256"; return 0; }
+  for (int l = 0; l < d.n_layers; ++l) {
+    if (d.dims[l] % 64 || d.dims[l] > kMaxW || d.dims[l] < 64) { *why = "layer input width must be a multiple of 64 in [64,512]"; return 0; }
+    const int N = d.dims[l + 1];
+    if (N % 32 || N > kMaxW || N < 32) { *why = "layer output width must be a multiple of 32 in [32,512]"; return 0; }
+  }
+  if (B % (128 * CG)) { *why = "batch must be a multiple of 256"; return 0; }
+  return 1;
+}
+
+int run_f16(estk_ctx* ctx, EvalF16Params& p, cudaStream_t stream, const char* who) {
+  const char* why = "";
+  if (!f16_supported(p.desc, p.B, &why)) {
+    estk_set_error("%s: shape not supported by the tcgen05 path (%s)", who, why);
+    return ESTK_ERR_UNSUPPORTED;
+  }
+  ESTK_CHECK_ARG(p.pairs >= 1 && p.pairs <= ESTK_MAX_POPULATION / 2, "%s: pairs=%d", who, p.pairs);
+  ESTK_CHECK_ARG((((uintptr_t)p.theta) & 31u) == 0, "%s: theta must be 32-byte aligned (256-bit loads)", who);
+  p.chunks = p.B / (128 * CG);
+  ESTK_CHECK_ARG(p.chunks * CG <= kEvalMaxChunks, "%s: batch too large", who);
+  p.n_centre = p.centre_out ? p.chunks : 0;
+  ESTK_CHECK_ARG(!p.centre_out || p.pairs * 2 < ESTK_MAX_POPULATION, "%s: population too large to fold the centre task", who);
+  p.n_tasks = p.n_centre + p.pairs * p.n_signs * p.chunks;
+  p.partial = ctx->eval_partial;
+  p.counters = ctx->counters;
+#ifdef ESTK_TC_PROFILE
+  { const char* e = getenv("ESTK_TC_PROFILE"); p.prof = e ? atoi(e) : 0; }
+#endif
+  const size_t smem = f16_smem_bytes();
+  ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int clusters = ctx->sm_count / CG;
+  if (clusters > p.n_tasks) clusters = p.n_tasks;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_f16_kernel, p));
+  return ESTK_OK;
+}
+
+}  // namespace
+
+// entry points used by estk_eval_mlp_tc.cu's estk_eval_mlp_f16 / estk_eval_mlp_center_f16
+int estk_f16v2_supported(const estk_mlp_desc* desc, int B) {
+  const char* why = "";
+  return f16_supported(*desc, B, &why);
+}
+
+int estk_f16v2_eval(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta, const float* table,
+                    const uint16_t* table16, const int64_t* offsets, const int32_t* order, int32_t pairs, float sigma,
+                    const float* obs, const float* target, int32_t B, float* returns_plus, float* returns_minus,
+                    float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim, float* centre_return_out,
+                    int n_signs, cudaStream_t stream, const char* who) {
+  EvalF16Params p = {};
+  p.desc = *desc; p.theta = theta; p.table = table; p.table16 = table16;
+  p.offsets = offsets; p.order = order;
+  p.pairs = pairs; p.sigma = sigma; p.obs = obs; p.target = target; p.B = B;
+  p.ret_plus = returns_plus; p.ret_minus = returns_minus;
+  p.bc_plus = bc_plus; p.bc_minus = bc_minus; p.bc_obs = bc_obs; p.bc_dim = bc_dim;
+  p.n_signs = n_signs; p.centre_out = centre_return_out;
+  return run_f16(ctx, p, stream, who);
+}
+
+#ifdef ESTK_TC_PROFILE
+// triage builds only (not part of estk.h): read and clear the role counters
+extern "C" __attribute__((visibility("default"))) int estk_debug_f16_profile(unsigned long long* host_out, int n) {
+  if (n > 32) n = 32;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(host_out, g_f16_prof, sizeof(unsigned long long) * n) != cudaSuccess) return -1;
+  unsigned long long zeros[32] = {};
+  return cudaMemcpyToSymbol(g_f16_prof, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -1;
+}
+#endif

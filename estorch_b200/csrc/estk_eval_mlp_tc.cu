@@ -42,10 +42,7 @@
 // from L2).  Measured and rejected (profiles/README.md): L2 bulk-prefetch warp, 2-k-block
 // ring stages, register-pipelined producer refill, 8 epilogue + 6 producer warps,
 // 16-column double-buffered TMEM drains, bias fetched a layer ahead / by a 15th warp.
-#include "estk_common.cuh"
-#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
+#include "estk_tc.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -53,9 +50,6 @@ __device__ unsigned long long g_tc_prof[32];   // ESTK_TC_DEBUG bit 8: per-role 
 
 namespace {
 
-constexpr int kMaxW = 512;            // max layer width (K and N) of this path
-constexpr int kBlockK = 64;           // bf16 elements per 128-byte swizzle row
-constexpr int kKBlockBytes = 128 * kBlockK * 2;   // one [128 x 64] bf16 tile = 16 KB
 constexpr int kStageBytes = kKBlockBytes;          // B ring stage = one k-block: [<=128 rows x 64] at CG=2
                                                    // (two k-blocks per stage were measured: no gain, less ring depth)
 constexpr int kNumEpiWarps = 4, kNumProdWarps = 8;
@@ -104,208 +98,6 @@ struct EvalTCParams {
   int mode;                // kModeBF16 / kModeBF16S / kModeF16
   int dbg;                 // ESTK_TC_DEBUG bit mask (perf triage only): 1 no producer loads, 4 no MMA, 8 role counters, 16 TMEM read only
 };
-
-// ------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-// mbarrier waits use the CTA-scope form: ptxas pairs a cluster-scope acquire with
-// CCTL.IVALL (L1 invalidate + drain of outstanding loads)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
-template <int CG>
-__device__ __forceinline__ void mbar_arrive_on(uint32_t bar, uint32_t cta) {
-  if constexpr (CG == 1) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-  } else {
-    asm volatile(
-        "{\n"
-        ".reg .b32 ra;\n"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
-        "}" ::"r"(bar), "r"(cta) : "memory");
-  }
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// 2-D tiled TMA load into this CTA's shared memory, completion on this CTA's mbarrier
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-// generic-proxy st.shared -> visible to the async proxy (tensor core reads of smem)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred P;\n"
-      "elect.sync _|P, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, P;\n"
-      "}" : "=r"(pred));
-  return pred != 0;
-}
-template <int CG>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  if constexpr (CG == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-}
-template <int CG>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  if constexpr (CG == 1)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-  else
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
-template <int CG>
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                          uint32_t idesc, uint32_t accumulate) {
-  if constexpr (CG == 1) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
-        "r"(idesc), "r"(accumulate) : "memory");
-  } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
-        "r"(idesc), "r"(accumulate) : "memory");
-  }
-}
-// all previously issued MMAs complete -> arrive (once) on `bar` in every CTA of the pair
-template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  if constexpr (CG == 1) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-  } else {
-    const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-  }
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// 16 packed-bf16x2 words per lane back into TMEM (the activation stash, see the epilogue)
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint4 ld_noise4u(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-
-// UMMA shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-//  version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64)).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
-// K-major A and B, n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29).
-// (a/b format 0 = F16, 1 = BF16)
-__device__ __forceinline__ uint32_t make_idesc(int M, int N, bool f16) {
-  const uint32_t fmt = f16 ? 0u : ((1u << 7) | (1u << 10));
-  return (1u << 4) | fmt | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-// byte offset of the 16-byte chunk (row r, chunk c8 of 8 bf16) inside a swizzled [rows x 64] tile
-__device__ __forceinline__ uint32_t sw128_offset(int r, int c8) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-// relu(x) rounded to bf16, two at a time (ReLU fused into the conversion)
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-// fp16 variants (saturating: an activation beyond +-65504 becomes +-65504, not inf)
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint32_t pack_f16_relu(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ float2 unpack_f16(uint32_t h2) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&h2));
-}
-template <bool F16> __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
-  return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
-}
-template <bool F16> __device__ __forceinline__ uint32_t pack16_relu(float lo, float hi) {
-  return F16 ? pack_f16_relu(lo, hi) : pack_bf16_relu(lo, hi);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4u(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 struct Layer { int K, N; int64_t wbase, bbase; };
 
@@ -1097,7 +889,19 @@ extern "C" int estk_eval_mlp_center_bf16s(estk_ctx* ctx, const estk_mlp_desc* de
   return run_tc(ctx, p, (cudaStream_t)stream, "estk_eval_mlp_center_bf16s");
 }
 
-// ---- fp16 operands from fp32 theta + the exact 16-bit noise table (the default tensor-core mode)
+// ---- fp16 operands from fp32 theta + the exact 16-bit noise table (the default tensor-core mode).
+// The product kernel is the warpgroup-specialised one in estk_eval_mlp_f16.cu; the kModeF16
+// instantiation of the kernel above is kept as an A/B reference (ESTK_F16_V1=1, triage only).
+int estk_f16v2_supported(const estk_mlp_desc* desc, int B);
+int estk_f16v2_eval(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta, const float* table,
+                    const uint16_t* table16, const int64_t* offsets, const int32_t* order, int32_t pairs, float sigma,
+                    const float* obs, const float* target, int32_t B, float* returns_plus, float* returns_minus,
+                    float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim, float* centre_return_out,
+                    int n_signs, cudaStream_t stream, const char* who);
+static bool f16_use_v1() {
+  static const bool v1 = [] { const char* e = getenv("ESTK_F16_V1"); return e && atoi(e) != 0; }();
+  return v1;
+}
 __global__ void __launch_bounds__(256) shadow_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4,
                                                          unsigned long long* __restrict__ inexact) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1138,6 +942,10 @@ extern "C" int estk_eval_mlp_f16(estk_ctx* ctx, const estk_mlp_desc* desc, const
   ESTK_CHECK_ARG((bc_plus == nullptr) == (bc_minus == nullptr), "estk_eval_mlp_f16: bc_plus/bc_minus must both be set or both null");
   ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(table) && ESTK_ALIGNED16(obs) && ESTK_ALIGNED16(target) &&
                  ESTK_ALIGNED16(table16), "estk_eval_mlp_f16: buffers must be 16-byte aligned");
+  if (!f16_use_v1())
+    return estk_f16v2_eval(ctx, desc, theta, table, table16, offsets, order, pairs, sigma, obs, target, B, returns_plus,
+                           returns_minus, bc_plus, bc_minus, bc_obs, bc_dim, centre_return_out, 2, (cudaStream_t)stream,
+                           "estk_eval_mlp_f16");
   EvalTCParams p = {};
   p.desc = *desc; p.theta = theta; p.table = table; p.table16 = table16;
   p.offsets = offsets; p.order = order;
@@ -1154,6 +962,9 @@ extern "C" int estk_eval_mlp_center_f16(estk_ctx* ctx, const estk_mlp_desc* desc
   ESTK_CHECK_ARG(ctx && desc && theta && obs && target && return_out, "estk_eval_mlp_center_f16: null argument");
   ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(obs) && ESTK_ALIGNED16(target),
                  "estk_eval_mlp_center_f16: buffers must be 16-byte aligned");
+  if (!f16_use_v1())
+    return estk_f16v2_eval(ctx, desc, theta, theta, nullptr, nullptr, nullptr, 1, 0.f, obs, target, B, return_out, nullptr,
+                           bc_out, nullptr, bc_obs, bc_dim, nullptr, 1, (cudaStream_t)stream, "estk_eval_mlp_center_f16");
   EvalTCParams p = {};
   p.desc = *desc; p.theta = theta; p.table = theta; p.offsets = nullptr; p.order = nullptr;
   p.pairs = 1; p.sigma = 0.f; p.obs = obs; p.target = target; p.B = B;
@@ -1165,6 +976,7 @@ extern "C" int estk_eval_mlp_center_f16(estk_ctx* ctx, const estk_mlp_desc* desc
 
 extern "C" int estk_eval_mlp_f16_supported(const estk_mlp_desc* desc, int32_t B) {
   const char* why = "";
+  if (desc && !f16_use_v1()) return estk_f16v2_supported(desc, B);
   return desc ? tc_supported(*desc, B, 2, &why, kModeF16) : 0;
 }
 

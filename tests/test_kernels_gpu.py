@@ -35,13 +35,19 @@ def test_fill_noise_table_matches_oracle(be):
     be.fill_noise_table(t, 42)
     got = t.cpu().numpy()
     want = orc.philox_normal_table(n, 42)
-    # fp32 log/sincos differ by ulps between libm and the device: |z| < 6
-    assert np.max(np.abs(got - want)) < 2e-5
+    # every entry is fp16-representable (so that the 16-bit copy of the table is exact) ...
+    np.testing.assert_array_equal(got, got.astype(np.float16).astype(np.float32))
+    # ... and equals the oracle's Philox + Box-Muller value rounded to fp16; fp32 log/sincos differ
+    # by ulps between libm and the device, which can move an entry across an fp16 rounding boundary:
+    # at most one fp16 ulp (2^-8 for |z| < 8), and rarely
+    diff = np.abs(got - want)
+    assert diff.max() <= 2.0 ** -8 and np.count_nonzero(diff) < n // 50
     big = be.alloc(1 << 24)
     be.fill_noise_table(big, (7 << 32) | 9)
     assert abs(float(big.mean())) < 2e-3 and abs(float(big.std()) - 1.0) < 2e-3
     assert torch.isfinite(big).all()
-    np.testing.assert_allclose(big[:4096].cpu().numpy(), orc.philox_normal_table(4096, (7 << 32) | 9), atol=2e-5)
+    d2 = np.abs(big[:4096].cpu().numpy() - orc.philox_normal_table(4096, (7 << 32) | 9))
+    assert d2.max() <= 2.0 ** -8 and np.count_nonzero(d2) < 4096 // 50
 
 
 @pytest.mark.parametrize("pairs,n,table_len,pair_begin,gen", [
