@@ -42,7 +42,7 @@ struct estk_ctx {
   float* cvals;            // [ESTK_MAX_POPULATION] blended centred ranks (fp32)
   float* partial;          // [max_grid * 1024] split-over-pairs partial sums
   float* eval_partial;     // [ESTK_MAX_POPULATION * kEvalMaxChunks] loss partials
-  unsigned int* counters;  // [ESTK_MAX_POPULATION] self-resetting arrival counters
+  unsigned int* counters;  // [ESTK_MAX_POPULATION + 8] self-resetting arrival counters (+ kernel tickets)
   double* scalars;         // [8] small fp64 scratch (||archive||_F, ...)
 };
 static const int kEvalMaxChunks = 64;
@@ -67,6 +67,14 @@ __device__ __forceinline__ float4 ld_noise4(const float4* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+// the same for the fp16 copy of the table: 8 values per 128-bit load
+__device__ __forceinline__ uint4 ld_noise4h(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
   return v;
 }

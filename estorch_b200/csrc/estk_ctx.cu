@@ -42,9 +42,9 @@ extern "C" int estk_ctx_create(int device, estk_ctx** out) {
   if (e == cudaSuccess) e = cudaMalloc(&c->partial, sizeof(float) * (size_t)c->max_grid * 1024);
   if (e == cudaSuccess)
     e = cudaMalloc(&c->eval_partial, sizeof(float) * (size_t)ESTK_MAX_POPULATION * kEvalMaxChunks);
-  if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(unsigned int) * ESTK_MAX_POPULATION);
+  if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(unsigned int) * (ESTK_MAX_POPULATION + 8));
   if (e == cudaSuccess) e = cudaMalloc(&c->scalars, sizeof(double) * 8);
-  if (e == cudaSuccess) e = cudaMemset(c->counters, 0, sizeof(unsigned int) * ESTK_MAX_POPULATION);
+  if (e == cudaSuccess) e = cudaMemset(c->counters, 0, sizeof(unsigned int) * (ESTK_MAX_POPULATION + 8));
   if (e != cudaSuccess) {
     estk_set_error("estk_ctx_create: workspace allocation failed: %s", cudaGetErrorString(e));
     estk_ctx_destroy(c);

@@ -7,24 +7,28 @@
 // deep-copies state_dict(); here theta -> best_theta on the device), then
 // `self.step += 1` (:248).  Every thread evaluates the same predicate from the
 // same two scalars, thread 0 of block 0 publishes the new state afterwards.
-__global__ void __launch_bounds__(256) track_best_copy_kernel(const estk_state* state,
-                                                              const float* __restrict__ reward,
-                                                              const float* __restrict__ theta,
-                                                              float* __restrict__ best_theta,
-                                                              int64_t n) {
+__global__ void __launch_bounds__(256) track_best_kernel(estk_state* state, const float* __restrict__ reward,
+                                                         const float* __restrict__ theta,
+                                                         float* __restrict__ best_theta, int64_t n,
+                                                         unsigned int* ticket) {
   const float r = __ldg(reward);
-  if (!(r > state->best_reward)) return;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
-    best_theta[k] = theta[k];
-}
-__global__ void track_best_commit_kernel(estk_state* state, const float* __restrict__ reward) {
-  const float r = __ldg(reward);
-  state->episode_reward = r;
-  const bool better = r > state->best_reward;
-  if (better) state->best_reward = r;
-  state->improved = better ? 1 : 0;
-  state->generation += 1;
+  const bool better = r > state->best_reward;          // read by every CTA before it takes a ticket
+  if (better) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+      best_theta[k] = theta[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {       // last CTA: publish the new state
+      state->episode_reward = r;
+      if (better) state->best_reward = r;
+      state->improved = better ? 1 : 0;
+      state->generation += 1;
+      *ticket = 0u;
+    }
+  }
 }
 
 extern "C" int estk_track_best(estk_ctx* ctx, estk_state* state, const float* reward,
@@ -32,9 +36,8 @@ extern "C" int estk_track_best(estk_ctx* ctx, estk_state* state, const float* re
   ESTK_CHECK_ARG(ctx && state && reward && theta && best_theta && n > 0, "estk_track_best: bad argument");
   int blocks = (int)((n + 255) / 256);
   if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
-  track_best_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(state, reward, theta, best_theta, n);
-  ESTK_CUDA(cudaGetLastError());
-  track_best_commit_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, reward);
+  track_best_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(state, reward, theta, best_theta, n,
+                                                             ctx->counters + ESTK_MAX_POPULATION + 1);
   ESTK_CUDA(cudaGetLastError());
   return ESTK_OK;
 }

@@ -26,7 +26,7 @@
 //            (deterministic; no atomics anywhere).
 #include "estk_common.cuh"
 #include <cooperative_groups.h>
-#include <stdlib.h>
+#include <cuda_fp16.h>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -39,7 +39,10 @@ struct RankGradParams {
   float w_rew, w_nov;
   int P, pairs;          // global population / pair count
   int pair_begin, pairs_local;
-  const float* table;
+  const float* table;      // fp32 table, or null when table16 is given
+  const uint16_t* table16; // exact fp16 copy of the table (half the bytes, identical values)
+  int world;               // > 1: `returns` / `novelty` are laid out rank-major [world][2][pairs/world]
+                           // (the all-gather of each rank's (+,-) halves, no re-ordering copy)
   const int64_t* offsets;  // [pairs_local]
   const int32_t* order;    // [pairs_local] nullable
   int64_t n, n4;
@@ -123,7 +126,7 @@ __device__ __forceinline__ void epilogue(const RankGradParams& p, const AdamScal
   }
 }
 
-template <int NC, int T, int LOADS = 8>
+template <int NC, int T, int LOADS = 8, bool T16 = false>
 __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
   constexpr int kThreads = T;
   cg::grid_group grid = cg::this_grid();
@@ -162,20 +165,27 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
     const int warps = kThreads >> 5;
     const int gwarp = blockIdx.x * warps + (tid >> 5);
     const int nwarps = gridDim.x * warps;
+    // member index <-> position in `returns` (identity on one GPU; rank-major otherwise)
+    const int pl = p.pairs / max(p.world, 1);
+    auto pos_of = [&](int m) { const int sg = m / p.pairs, g = m % p.pairs; return ((g / pl) * 2 + sg) * pl + g % pl; };
+    auto member_of = [&](int q) { const int r = q / (2 * pl), rem = q - r * 2 * pl; return (rem / pl) * p.pairs + r * pl + rem % pl; };
     for (int i = gwarp; i < p.P; i += nwarps) {
-      const float ri = __ldg(p.returns + i);
+      const int pi = p.world > 1 ? pos_of(i) : i;
+      const float ri = __ldg(p.returns + pi);
       int cnt = 0;
       for (int j = lane; j < p.P; j += 32) {
         const float rj = __ldg(p.returns + j);
-        cnt += (rj < ri) || (rj == ri && j < i);
+        const int mj = p.world > 1 ? member_of(j) : j;
+        cnt += (rj < ri) || (rj == ri && mj < i);
       }
       cnt = warp_sum_i(cnt);
       int cnt2 = 0;
       if (p.novelty) {
-        const float qi = __ldg(p.novelty + i);
+        const float qi = __ldg(p.novelty + pi);
         for (int j = lane; j < p.P; j += 32) {
           const float qj = __ldg(p.novelty + j);
-          cnt2 += (qj < qi) || (qj == qi && j < i);
+          const int mj = p.world > 1 ? member_of(j) : j;
+          cnt2 += (qj < qi) || (qj == qi && mj < i);
         }
         cnt2 = warp_sum_i(cnt2);
       }
@@ -201,9 +211,80 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
   const int64_t c1 = (int64_t)(cs + 1) * p.n4 / p.CS;
   const int s0 = (int)((int64_t)ps * p.pairs_local / p.PS);
   const int s1 = (int)((int64_t)(ps + 1) * p.pairs_local / p.PS);
-  const float4* tab4 = reinterpret_cast<const float4*>(p.table);
   const AdamScalars adam = s_adam;  // valid: written before the __syncthreads in grid.sync
-
+  if constexpr (T16) {
+    // fp16 table: a 128-bit load carries 8 noise values; same 16 loads in flight per thread, half the
+    // bytes per pair row.  Columns are counted in vectors of 8 elements (p.n4 holds ceil(n/8) here).
+    const uint4* tab8 = reinterpret_cast<const uint4*>(p.table16);
+    for (int64_t cbase = c0; cbase < c1; cbase += (int64_t)kThreads * NC) {
+      int64_t col[NC];
+      bool act[NC];
+      float acc[NC][8];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        col[c] = cbase + (int64_t)c * kThreads + tid;
+        act[c] = col[c] < c1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+      }
+      for (int sbase = s0; sbase < s1; sbase += kPairTile) {
+        const int cnt = min(kPairTile, s1 - sbase);
+        __syncthreads();
+        for (int t = tid; t < cnt; t += kThreads) {
+          const int jl = p.order ? p.order[sbase + t] : (sbase + t);
+          const int jg = p.pair_begin + jl;
+          s_w[t] = __fsub_rn(__ldcg(p.cvals + jg), __ldcg(p.cvals + jg + p.pairs));
+          s_off4[t] = (uint32_t)(p.offsets[jl] >> 3);
+        }
+        __syncthreads();
+        constexpr int U = LOADS / NC;
+        auto fma8 = [&](float (&a)[8], float w, const uint4& t) {
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+          const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t.z));
+          const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&t.w));
+          a[0] = fmaf(w, f0.x, a[0]); a[1] = fmaf(w, f0.y, a[1]); a[2] = fmaf(w, f1.x, a[2]); a[3] = fmaf(w, f1.y, a[3]);
+          a[4] = fmaf(w, f2.x, a[4]); a[5] = fmaf(w, f2.y, a[5]); a[6] = fmaf(w, f3.x, a[6]); a[7] = fmaf(w, f3.y, a[7]);
+        };
+        int jj = 0;
+        for (; jj + U <= cnt; jj += U) {
+          uint4 t[U][NC];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+              if (act[c]) t[u][c] = ld_noise4h(tab8 + (size_t)s_off4[jj + u] + col[c]);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float w = s_w[jj + u];
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+              if (act[c]) fma8(acc[c], w, t[u][c]);
+          }
+        }
+        for (; jj < cnt; ++jj) {
+          const float w = s_w[jj];
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            if (act[c]) fma8(acc[c], w, ld_noise4h(tab8 + (size_t)s_off4[jj] + col[c]));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (!act[c]) continue;
+        const float4 lo = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+        const float4 hi = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+        if (p.PS == 1) {
+          epilogue(p, adam, col[c] * 2, lo);
+          if (col[c] * 8 + 4 < p.n) epilogue(p, adam, col[c] * 2 + 1, hi);
+        } else {
+          float4* part = reinterpret_cast<float4*>(p.partial) + ((int64_t)ps * p.n4 + col[c]) * 2;
+          part[0] = lo; part[1] = hi;
+        }
+      }
+    }
+  } else {
+  const float4* tab4 = reinterpret_cast<const float4*>(p.table);
   for (int64_t cbase = c0; cbase < c1; cbase += (int64_t)kThreads * NC) {
     int64_t col[NC];
     bool act[NC];
@@ -270,16 +351,20 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
       }
     }
   }
+  }
 
-  // ---- phase C: fixed-order sum of the pair-split partials
+  // ---- phase C: fixed-order sum of the pair-split partials (float4 granularity in both layouts:
+  //      the fp16-table path stores two float4 per 8-element vector)
   if (p.PS > 1) {
     __threadfence();
     grid.sync();
+    const int64_t nq = T16 ? p.n4 * 2 : p.n4;        // float4 columns per partial row
     const int64_t gstride = (int64_t)gridDim.x * kThreads;
-    for (int64_t col4 = (int64_t)blockIdx.x * kThreads + tid; col4 < p.n4; col4 += gstride) {
+    for (int64_t col4 = (int64_t)blockIdx.x * kThreads + tid; col4 < nq; col4 += gstride) {
+      if (col4 * 4 >= p.n) continue;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int q = 0; q < p.PS; ++q) {
-        const float4 t = __ldcg(reinterpret_cast<const float4*>(p.partial) + (int64_t)q * p.n4 + col4);
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(p.partial) + (int64_t)q * nq + col4);
         s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
       }
       epilogue(p, adam, col4, s);
@@ -288,7 +373,7 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
   if (p.fused_adam && blockIdx.x == 0 && tid == 0) p.state->adam_step = adam_t;
 }
 
-__global__ void __launch_bounds__(256) clamp_adam_kernel(const RankGradParams p) {
+__global__ void __launch_bounds__(256) clamp_adam_kernel(const RankGradParams p, unsigned int* ticket) {
   __shared__ AdamScalars s_adam;
   const bool do_adam = p.theta != nullptr;
   int64_t adam_t = 0;
@@ -325,16 +410,25 @@ __global__ void __launch_bounds__(256) clamp_adam_kernel(const RankGradParams p)
       p.grad_out[k] = gp;
     }
   }
+  // every CTA read adam_step before taking a ticket, so the last one to finish may publish the
+  // incremented counter (no CTA can observe it) and re-arm the ticket
+  if (do_adam) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        p.state->adam_step = adam_t;
+        *ticket = 0u;
+      }
+    }
+  }
 }
-// The step counter is advanced by a separate 1-thread epilogue so that no CTA
-// of clamp_adam_kernel can observe the incremented value.
-__global__ void bump_adam_step_kernel(estk_state* state) { state->adam_step += 1; }
 
-template <int NC, int T, int LOADS = 8>
+template <int NC, int T, int LOADS = 8, bool T16 = false>
 int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   constexpr int kThreads = T;
   int occ = 0;
-  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC, T, LOADS>, kThreads, 0));
+  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC, T, LOADS, T16>, kThreads, 0));
   if (occ < 1) {
     estk_set_error("rank_grad_kernel<%d> cannot be resident", NC);
     return ESTK_ERR_CUDA;
@@ -353,18 +447,18 @@ int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
     if (ps > ps_cap) ps = ps_cap;
     if (ps < 1) ps = 1;
     p.PS = ps;
-    if ((int64_t)p.PS * n4 * 4 > (int64_t)ctx->max_grid * 1024) {
+    if ((int64_t)p.PS * n4 * (T16 ? 8 : 4) > (int64_t)ctx->max_grid * 1024) {
       estk_set_error("rank_grad: partial workspace too small (PS=%d n4=%lld)", p.PS, (long long)n4);
       return ESTK_ERR_NOMEM;
     }
   }
   const int grid = p.CS * p.PS;
   void* args[] = {(void*)&p};
-  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC, T, LOADS>, dim3(grid), dim3(kThreads), args, 0, stream));
+  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC, T, LOADS, T16>, dim3(grid), dim3(kThreads), args, 0, stream));
   return ESTK_OK;
 }
 
-int check_common(estk_ctx* ctx, const float* returns, int P, const float* table,
+int check_common(estk_ctx* ctx, const float* returns, int P, const void* table,
                  const int64_t* offsets, int64_t n, const char* who) {
   ESTK_CHECK_ARG(ctx && returns && table && offsets, "%s: null argument", who);
   ESTK_CHECK_ARG(P >= 2 && (P % 2) == 0 && P <= ESTK_MAX_POPULATION,
@@ -378,27 +472,25 @@ int dispatch(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   // Large n: 512-thread CTAs, four float4 columns per thread (one CTA per SM), so that a CTA
   // covers its whole column slice in ONE pass over the (offset-sorted) pair list -- all CTAs then
   // walk the table in lock-step, which is what makes overlapping rows hit L2.
-  const char* force = getenv("ESTK_RG_VARIANT");            // perf triage only
-  const int variant = force ? atoi(force) : 0;
-  if (p.n4 >= (int64_t)ctx->sm_count * 512) {
-    if (variant == 1) return launch_rank_grad<2, 256>(ctx, p, stream);
-    if (variant == 2) return launch_rank_grad<2, 512>(ctx, p, stream);
-    if (variant == 3) return launch_rank_grad<4, 512, 8>(ctx, p, stream);
-    if (variant == 4) return launch_rank_grad<4, 384, 24>(ctx, p, stream);
-    return launch_rank_grad<4, 512, 16>(ctx, p, stream);   // 16 x 16 B in flight per thread = 128 KB per SM
+  if (p.table16) {                     // fp16 table: columns are 8-element vectors
+    p.n4 = (p.n + 7) / 8;
+    if (p.n4 >= (int64_t)ctx->sm_count * 512) return launch_rank_grad<2, 512, 16, true>(ctx, p, stream);
+    return launch_rank_grad<1, 256, 8, true>(ctx, p, stream);
   }
+  if (p.n4 >= (int64_t)ctx->sm_count * 512)
+    return launch_rank_grad<4, 512, 16>(ctx, p, stream);   // 16 x 16 B in flight per thread = 128 KB per SM
   return launch_rank_grad<1, 256>(ctx, p, stream);
 }
 
 }  // namespace
 
-extern "C" int estk_rank_grad_adam(estk_ctx* ctx, const float* returns, const float* novelty,
-                                   float w_rew, float w_nov, int32_t P, const float* table,
-                                   const int64_t* offsets, const int32_t* order, int64_t n,
-                                   float* theta, float* m, float* v, estk_state* state,
-                                   const estk_adam_desc* adam, int32_t* ranks_out,
-                                   int32_t* ranks2_out, float* grad_out, void* stream) {
-  int rc = check_common(ctx, returns, P, table, offsets, n, "estk_rank_grad_adam");
+static int rank_grad_adam_impl(estk_ctx* ctx, const float* returns, const float* novelty,
+                               float w_rew, float w_nov, int32_t P, const float* table, const uint16_t* table16,
+                               const int64_t* offsets, const int32_t* order, int64_t n,
+                               float* theta, float* m, float* v, estk_state* state,
+                               const estk_adam_desc* adam, int32_t* ranks_out,
+                               int32_t* ranks2_out, float* grad_out, void* stream) {
+  int rc = check_common(ctx, returns, P, table ? (const void*)table : (const void*)table16, offsets, n, "estk_rank_grad_adam");
   if (rc) return rc;
   ESTK_CHECK_ARG(theta && m && v && state && adam, "estk_rank_grad_adam: null optimizer argument");
   ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(m) && ESTK_ALIGNED16(v) &&
@@ -407,7 +499,7 @@ extern "C" int estk_rank_grad_adam(estk_ctx* ctx, const float* returns, const fl
   RankGradParams p = {};
   p.returns = returns; p.novelty = novelty; p.w_rew = w_rew; p.w_nov = w_nov;
   p.P = P; p.pairs = P / 2; p.pair_begin = 0; p.pairs_local = P / 2;
-  p.table = table; p.offsets = offsets; p.order = order;
+  p.table = table; p.table16 = table16; p.world = 1; p.offsets = offsets; p.order = order;
   p.n = n; p.n4 = (n + 3) / 4;
   p.cvals = ctx->cvals; p.partial = ctx->partial;
   p.ranks_out = ranks_out; p.ranks2_out = ranks2_out;
@@ -416,26 +508,69 @@ extern "C" int estk_rank_grad_adam(estk_ctx* ctx, const float* returns, const fl
   return dispatch(ctx, p, (cudaStream_t)stream);
 }
 
-extern "C" int estk_rank_grad(estk_ctx* ctx, const float* returns, const float* novelty,
-                              float w_rew, float w_nov, int32_t P, const float* table,
-                              const int64_t* offsets, const int32_t* order, int32_t pair_begin,
-                              int32_t pairs_local, int64_t n, float* grad_sum_out,
-                              int32_t* ranks_out, int32_t* ranks2_out, void* stream) {
-  int rc = check_common(ctx, returns, P, table, offsets, n, "estk_rank_grad");
+extern "C" int estk_rank_grad_adam(estk_ctx* ctx, const float* returns, const float* novelty,
+                                   float w_rew, float w_nov, int32_t P, const float* table,
+                                   const int64_t* offsets, const int32_t* order, int64_t n,
+                                   float* theta, float* m, float* v, estk_state* state,
+                                   const estk_adam_desc* adam, int32_t* ranks_out,
+                                   int32_t* ranks2_out, float* grad_out, void* stream) {
+  ESTK_CHECK_ARG(table != nullptr, "estk_rank_grad_adam: null table");
+  return rank_grad_adam_impl(ctx, returns, novelty, w_rew, w_nov, P, table, nullptr, offsets, order, n, theta, m, v,
+                             state, adam, ranks_out, ranks2_out, grad_out, stream);
+}
+
+extern "C" int estk_rank_grad_adam_h(estk_ctx* ctx, const float* returns, const float* novelty,
+                                     float w_rew, float w_nov, int32_t P, const uint16_t* table16,
+                                     const int64_t* offsets, const int32_t* order, int64_t n,
+                                     float* theta, float* m, float* v, estk_state* state,
+                                     const estk_adam_desc* adam, int32_t* ranks_out,
+                                     int32_t* ranks2_out, float* grad_out, void* stream) {
+  ESTK_CHECK_ARG(table16 != nullptr, "estk_rank_grad_adam_h: null table16");
+  return rank_grad_adam_impl(ctx, returns, novelty, w_rew, w_nov, P, nullptr, table16, offsets, order, n, theta, m, v,
+                             state, adam, ranks_out, ranks2_out, grad_out, stream);
+}
+
+static int rank_grad_impl(estk_ctx* ctx, const float* returns, const float* novelty,
+                          float w_rew, float w_nov, int32_t P, int32_t world, const float* table, const uint16_t* table16,
+                          const int64_t* offsets, const int32_t* order, int32_t pair_begin,
+                          int32_t pairs_local, int64_t n, float* grad_sum_out,
+                          int32_t* ranks_out, int32_t* ranks2_out, void* stream) {
+  int rc = check_common(ctx, returns, P, table ? (const void*)table : (const void*)table16, offsets, n, "estk_rank_grad");
   if (rc) return rc;
+  ESTK_CHECK_ARG(world >= 1 && (P / 2) % world == 0, "estk_rank_grad: world=%d does not divide %d pairs", world, P / 2);
   ESTK_CHECK_ARG(grad_sum_out && ESTK_ALIGNED16(grad_sum_out), "estk_rank_grad: grad_sum_out null or unaligned");
   ESTK_CHECK_ARG(pair_begin >= 0 && pairs_local > 0 && pair_begin + pairs_local <= P / 2,
                  "estk_rank_grad: local pairs [%d,+%d) outside %d", pair_begin, pairs_local, P / 2);
   RankGradParams p = {};
   p.returns = returns; p.novelty = novelty; p.w_rew = w_rew; p.w_nov = w_nov;
   p.P = P; p.pairs = P / 2; p.pair_begin = pair_begin; p.pairs_local = pairs_local;
-  p.table = table; p.offsets = offsets; p.order = order;
+  p.table = table; p.table16 = table16; p.world = world; p.offsets = offsets; p.order = order;
   p.n = n; p.n4 = (n + 3) / 4;
   p.cvals = ctx->cvals; p.partial = ctx->partial;
   p.ranks_out = ranks_out; p.ranks2_out = ranks2_out;
   p.fused_adam = 0; p.grad_sum_out = grad_sum_out;
   p.adam.clamp = 0.f;
   return dispatch(ctx, p, (cudaStream_t)stream);
+}
+
+extern "C" int estk_rank_grad(estk_ctx* ctx, const float* returns, const float* novelty,
+                              float w_rew, float w_nov, int32_t P, const float* table,
+                              const int64_t* offsets, const int32_t* order, int32_t pair_begin,
+                              int32_t pairs_local, int64_t n, float* grad_sum_out,
+                              int32_t* ranks_out, int32_t* ranks2_out, void* stream) {
+  ESTK_CHECK_ARG(table != nullptr, "estk_rank_grad: null table");
+  return rank_grad_impl(ctx, returns, novelty, w_rew, w_nov, P, 1, table, nullptr, offsets, order, pair_begin,
+                        pairs_local, n, grad_sum_out, ranks_out, ranks2_out, stream);
+}
+
+extern "C" int estk_rank_grad_h(estk_ctx* ctx, const float* returns, const float* novelty,
+                                float w_rew, float w_nov, int32_t P, int32_t world, const uint16_t* table16,
+                                const int64_t* offsets, const int32_t* order, int32_t pair_begin,
+                                int32_t pairs_local, int64_t n, float* grad_sum_out,
+                                int32_t* ranks_out, int32_t* ranks2_out, void* stream) {
+  ESTK_CHECK_ARG(table16 != nullptr, "estk_rank_grad_h: null table16");
+  return rank_grad_impl(ctx, returns, novelty, w_rew, w_nov, P, world, nullptr, table16, offsets, order, pair_begin,
+                        pairs_local, n, grad_sum_out, ranks_out, ranks2_out, stream);
 }
 
 extern "C" int estk_clamp_adam(estk_ctx* ctx, const float* grad_sum, int32_t P, int64_t n,
@@ -452,11 +587,7 @@ extern "C" int estk_clamp_adam(estk_ctx* ctx, const float* grad_sum, int32_t P, 
   p.grad_out = grad_out; p.theta = theta; p.m = m; p.v = v; p.state = state; p.adam = *adam;
   int blocks = (int)((n + 255) / 256);
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-  clamp_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  clamp_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, ctx->counters + ESTK_MAX_POPULATION);
   ESTK_CUDA(cudaGetLastError());
-  if (do_adam) {
-    bump_adam_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
-    ESTK_CUDA(cudaGetLastError());
-  }
   return ESTK_OK;
 }
