@@ -15,13 +15,20 @@
 //   D[obs, out] = H[obs, in] * W_s[out, in]^T
 //   A  activations H: 128 rows per CTA, fp16, K-major, 128B-swizzled, RESIDENT in shared memory
 //      across layers (8 k-blocks x 16 KB, updated in place);
-//   B  W_s formed ON THE FLY into a 5-stage ring of [128 x 64] tiles (each CTA forms its half of
-//      the N tile) -- the perturbed weights never exist in global memory;
+//   B  W_s formed ON THE FLY in a ring of five 16 KB slots (each CTA forms its half of the N tile;
+//      the perturbed weights never exist in global memory).  Stage k = one [128 x 64] k-block:
+//      the TMA engine lands the fp32 theta tile as two [128 x 32] halves (SWIZZLE_128B) in slots
+//      A = 2k mod 5 and B = 2k+1 mod 5; the producers read both, add s*sigma*eps (noise through
+//      registers) and write the fp16 tile IN PLACE over half A -- a row of the fp16 tile occupies
+//      exactly the bytes of the same row of half A, and the eight lanes that own a row sit in one
+//      warp, so a __syncwarp separates the reads from the write.  Slot B is released at once, slot
+//      A by the MMA's commit.  Up to ~64 KB of theta are in flight per SM without holding a single
+//      register (measured: the L2 path needs ~1 KB in flight per GB/s and SM);
 //   D  the whole layer output [128 x <=512] fp32 in TMEM (512 columns) as two N tiles.
 // Warp roles (20 warps, homogeneous warpgroups so that setmaxnreg can move registers):
-//   WG0    w0 MMA issuer (leader CTA), w1 TMEM allocator, w2-3 idle           -> 40 registers
+//   WG0    w0 MMA issuer (leader CTA), w1 TMEM allocator + theta TMA thread, w2-3 idle -> 40 registers
 //   WG1-2  8 epilogue warps: two per TMEM lane quarter, each half of the columns -> 112
-//   WG3-4  8 weight producers in 2 groups of 4 warps (rolling 4-item load window)  -> 104
+//   WG3-4  8 weight producers in 2 groups of 4 warps (noise one stage ahead in registers) -> 104
 // Epilogue schedule per layer: tile 0 is drained while tile 1's MMAs still run (they read the
 // activations, which therefore cannot be overwritten yet) -- bias, ReLU, fp16, parked as packed
 // pairs in the TMEM columns the drain itself freed; when the layer is accumulated the parked half
@@ -48,8 +55,12 @@ __device__ unsigned long long g_f16_prof[32];   // per-role cycle counters of CT
 namespace {
 
 constexpr int CG = 2;                         // CTAs per cluster = tcgen05 cta_group
-constexpr int kStages = 5;                    // B ring depth (16 KB stages beside 128 KB of activations)
+constexpr int kSlots = 5;                     // 16 KB slots of the B ring (beside 128 KB of activations)
+constexpr int kStages = kSlots;
 constexpr int kStageBytes = kKBlockBytes;
+// TMA descriptors of the fp32 theta, one per (layer, N tile): [N x K] row-major, box [rows of the
+// tile per CTA x 32] (128 bytes), SWIZZLE_128B
+struct ThetaMaps { CUtensorMap m[ESTK_MAX_LAYERS][2]; };
 constexpr int kCtlWarps = 4, kEpiWarps = 8, kProdWarps = 8;
 constexpr int kEpiWarp0 = kCtlWarps, kProdWarp0 = kCtlWarps + kEpiWarps;
 constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, launched at 96 registers
@@ -105,19 +116,23 @@ __device__ __forceinline__ TaskId decode_task(const EvalF16Params& p, int task, 
   return t;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16Params p) {
+__global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16Params p,
+                                                                    const __grid_constant__ ThetaMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sH = smem;                                    // 8 k-blocks x 16 KB
   uint8_t* sB = sH + (kMaxW / kBlockK) * kKBlockBytes;   // ring
   float* sBias = reinterpret_cast<float*>(sB + kStages * kStageBytes);   // [2][512]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * kMaxW);
-  uint64_t* bar_full = bars;                   // [kStages]  weights of the stage formed        (leader's are used)
-  uint64_t* bar_empty = bars + kStages;        // [kStages]  stage consumed by the MMAs          (local)
-  uint64_t* bar_acc0 = bars + 2 * kStages;     // first N tile of a two-tile layer accumulated   (local)
-  uint64_t* bar_acc = bars + 2 * kStages + 1;  // layer accumulated                              (local)
-  uint64_t* bar_h = bars + 2 * kStages + 2;    // [2] next layer's k-blocks 0..3 / 4..7 in place (leader's are used)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  // per slot: what it holds alternates between "half A" (theta k 0..31, then the fp16 tile) and "half B"
+  uint64_t* bar_full = bars;                   // [kSlots]  fp16 tile formed in the slot           (leader's are used)
+  uint64_t* bar_emptyA = bars + kSlots;        // [kSlots]  tile consumed by the MMAs (tcgen05.commit) (local)
+  uint64_t* bar_emptyB = bars + 2 * kSlots;    // [kSlots]  half B read by the producers            (local)
+  uint64_t* bar_land = bars + 3 * kSlots;      // [kSlots]  both theta halves of the stage landed (on its A slot) (local)
+  uint64_t* bar_acc0 = bars + 4 * kSlots;      // first N tile of a two-tile layer accumulated   (local)
+  uint64_t* bar_acc = bars + 4 * kSlots + 1;   // layer accumulated                              (local)
+  uint64_t* bar_h = bars + 4 * kSlots + 2;     // [2] next layer's k-blocks 0..3 / 4..7 in place (leader's are used)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4 * kSlots + 4);
   float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kEpiWarps]
   __shared__ Layer lay[ESTK_MAX_LAYERS];
 
@@ -127,9 +142,11 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
   const int L = p.desc.n_layers;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       mbar_init(smem_u32(bar_full + s), CG * kProdGroupWarps);
-      mbar_init(smem_u32(bar_empty + s), 1);
+      mbar_init(smem_u32(bar_emptyA + s), 1);
+      mbar_init(smem_u32(bar_emptyB + s), kProdGroupWarps);
+      mbar_init(smem_u32(bar_land + s), 1);
     }
     mbar_init(smem_u32(bar_acc0), 1);
     mbar_init(smem_u32(bar_acc), 1);
@@ -162,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     setmaxnreg_dec<kRegsCtl>();
     if (warp == 0 && cta_rank == 0) {
       // =================================================================== MMA issuer
-      uint32_t stage = 0, ring_phase = 0, h_phase0 = 0, h_phase1 = 0;
+      uint32_t kst = 0, h_phase0 = 0, h_phase1 = 0;     // kst: global stage index
       const long long tm0 = PROF_T();
       for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
         for (int l = 0; l < L; ++l) {
@@ -187,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
                 tc_fence_after();
                 second_half_ready = true;
               }
+              const uint32_t stage = (2u * kst) % kSlots, ring_phase = (kst / kSlots) & 1u;   // the stage's A slot
               const long long tf0 = PROF_T();
               mbar_wait(smem_u32(bar_full + stage), ring_phase);
               PROF_ADD(2, tf0);
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
                   for (int k = 0; k < kBlockK / 16; ++k)
                     umma_bf16<CG>(tmem_d, make_sw128_desc(a_lo + k * 32), make_sw128_desc(b_addr + k * 32), idesc, 1u);
                 }
-                umma_commit<CG>(smem_u32(bar_empty + stage));          // frees the ring slot (both CTAs)
+                umma_commit<CG>(smem_u32(bar_emptyA + stage));         // frees the slot (both CTAs)
                 if (kb + 1 == K / kBlockK) {
                   if (n0 + 256 >= N) umma_commit<CG>(smem_u32(bar_acc));     // layer accumulated
                   else umma_commit<CG>(smem_u32(bar_acc0));                  // tile 0 of 2: its drain overlaps tile 1's MMAs
@@ -213,12 +231,36 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
               }
               __syncwarp();
               PROF_ADD(3, ti0);
-              if (++stage == kStages) { stage = 0; ring_phase ^= 1; }
+              ++kst;
             }
           }
         }
       }
       PROF_ADD(0, tm0);
+    } else if (warp == 1 && lane == 0) {
+      // =================================================================== theta TMA thread
+      // Walks the same (task, layer, n-tile, k-block) stage sequence as the producers; stage k gets
+      // slots A = 2k mod 5 and B = 2k+1 mod 5.  The last use of A was the B half of stage k-3 (freed by
+      // the producers), the last use of B the fp16 tile of stage k-2 (freed by the MMAs' commit).
+      uint32_t k = 0;
+      for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
+        for (int l = 0; l < L; ++l) {
+          const int K = lay[l].K, N = lay[l].N;
+          for (int n0 = 0; n0 < N; n0 += 256) {
+            const int rows = min(256, N - n0) / CG;
+            const CUtensorMap* map = &maps.m[l][n0 ? 1 : 0];
+            for (int kb = 0; kb < K / kBlockK; ++kb, ++k) {
+              const uint32_t sa = (2u * k) % kSlots, sb = (2u * k + 1u) % kSlots;
+              if (k >= 3) mbar_wait(smem_u32(bar_emptyB + sa), ((k - 3) / kSlots) & 1u);
+              if (k >= 2) mbar_wait(smem_u32(bar_emptyA + sb), ((k - 2) / kSlots) & 1u);
+              const uint32_t land = smem_u32(bar_land + sa);
+              mbar_arrive_expect_tx(land, (uint32_t)rows * 256u);
+              tma_load_2d(smem_u32(sB + sa * kStageBytes), map, kb * kBlockK, n0 + (int)cta_rank * rows, land);
+              tma_load_2d(smem_u32(sB + sb * kStageBytes), map, kb * kBlockK + 32, n0 + (int)cta_rank * rows, land);
+            }
+          }
+        }
+      }
     }
   } else if (warp < kProdWarp0) {
     // =================================================================== epilogue warps
@@ -440,25 +482,27 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     EPROF_ADD(10, te0);
   } else {
     // =================================================================== weight producers
-    // kProdGroups groups of warps; group g builds stages g, g+G, g+2G, ... of the flattened
-    // (task, layer, n-tile, k-block) stage sequence.  A thread owns 16-byte output chunks of the
-    // [rows x 64] tile: 8 weights = ONE 256-bit load of theta (fp32, L2 resident; a whole 32-byte
-    // sector per thread) + one 128-bit load of the noise row (fp16), W = rn_f16(theta + s*sigma*eps)
-    // with the sum in fp32, one swizzled 128-bit st.shared.  The loads run as a ROLLING window of
-    // kWin items per thread that continues across stage boundaries (the refill of a register set
-    // is issued right after its item has been converted; the ring-slot wait only gates the stores),
-    // so kWin * 48 bytes per thread are in flight all the time.
+    // kProdGroups groups of warps; group g converts stages g, g+G, g+2G, ... of the flattened
+    // (task, layer, n-tile, k-block) stage sequence.  A thread owns the 16-byte output chunk c8 of
+    // rows r0 + u*kRS of the [rows x 64] tile: 8 weights = 32 bytes of fp32 theta from the landing
+    // slots (k < 32: slot A, k >= 32: slot B; both 128B-swizzled like the fp16 tile) + 16 bytes of
+    // the noise row (fp16, a 128-bit global load issued one whole stage earlier),
+    // W = rn_f16(theta + s*sigma*eps) with the sum in fp32, written over the same row of slot A.
     setmaxnreg_inc<kRegsProd>();
     const int pwarp = warp - kProdWarp0;
     const int pgroup = pwarp / kProdGroupWarps;
     const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // thread index inside the group
     constexpr int kRS = kPT / 8;             // tile rows covered by one item step of the group
     constexpr int kIU = 128 / kRS;           // item steps per (full) stage
-    constexpr int kWin = 4;                  // items in flight per thread
-    static_assert(kIU >= kWin, "window larger than a stage");
     const int r0 = ptid >> 3, c8 = ptid & 7;
-    const uint32_t soff = sw128_offset(r0, c8);               // + u * kRS * 128 for item step u
-    struct St { const float* th; const uint16_t* ep; int k_rs; int rows; float sg; uint32_t sbase, stage, phase; };
+    // byte offsets inside a slot of the two 16-byte theta chunks this thread reads (row r0; rows
+    // r0 + u*kRS add u*kRS*128: kRS is a multiple of 8, the swizzle term does not change).  The
+    // lanes with c8 >= 4 read their pair in the opposite order: the eight lanes of a row then hit
+    // eight different 16-byte bank groups in each of the two ld.shared (no conflicts).
+    const int ch0 = 2 * (c8 & 3) + (c8 >> 2), ch1 = 2 * (c8 & 3) + 1 - (c8 >> 2);
+    const uint32_t roff0 = sw128_offset(r0, ch0), roff1 = sw128_offset(r0, ch1);
+    const uint32_t woff = sw128_offset(r0, c8);               // the fp16 output chunk
+    struct St { const uint16_t* ep; int k_rs; int rows; float sg; uint32_t kst; };
     int cached_task = -1;
     const uint16_t* cached_trow16 = nullptr;
     float cached_ssig = 0.f;
@@ -496,34 +540,17 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
       const int K = lay[l].K;
       d.rows = min(256, lay[l].N - n0) / CG;                   // this CTA's share of the B tile
       const int64_t rbase = lay[l].wbase + (int64_t)(n0 + (int)cta_rank * d.rows + r0) * K + kb * kBlockK + c8 * 8;
-      d.th = p.theta + rbase;
       d.ep = cached_trow16 ? cached_trow16 + rbase : nullptr;
       d.k_rs = K * kRS;
       d.sg = cached_ssig;
-      d.stage = counter % kStages;
-      d.phase = (counter / kStages) & 1u;
-      d.sbase = smem_u32(sB + d.stage * kStageBytes) + soff;
+      d.kst = counter;
     };
     bool has_cur = task < p.n_tasks;
     for (int sk = 0; sk < pgroup && has_cur; ++sk) has_cur = advance();
-    float T[kWin][8];
-    uint4 E[kWin];
-    auto load_item = [&](const St& d, int u, float (&t)[8], uint4& e) {
+    uint4 E[kIU];
+    auto load_eps = [&](const St& d, int u, uint4& e) {
       e = make_uint4(0u, 0u, 0u, 0u);
-      if (u * kRS + r0 < d.rows) {
-        ld_noise8(d.th + (size_t)u * d.k_rs, t);
-        if (d.ep) e = ld_noise4u(reinterpret_cast<const uint4*>(d.ep + (size_t)u * d.k_rs));
-      }
-    };
-    auto form_item = [&](const St& d, int u, const float (&t)[8], const uint4& e) {
-      if (u * kRS + r0 < d.rows) {
-        const float2 e0 = unpack_f16(e.x), e1 = unpack_f16(e.y), e2 = unpack_f16(e.z), e3 = unpack_f16(e.w);
-        const uint32_t w0 = pack_f16(fmaf(d.sg, e0.x, t[0]), fmaf(d.sg, e0.y, t[1]));
-        const uint32_t w1 = pack_f16(fmaf(d.sg, e1.x, t[2]), fmaf(d.sg, e1.y, t[3]));
-        const uint32_t w2 = pack_f16(fmaf(d.sg, e2.x, t[4]), fmaf(d.sg, e2.y, t[5]));
-        const uint32_t w3 = pack_f16(fmaf(d.sg, e3.x, t[6]), fmaf(d.sg, e3.y, t[7]));
-        st_shared_v4(d.sbase + (uint32_t)u * (kRS * 128), w0, w1, w2, w3);
-      }
+      if (d.ep && u * kRS + r0 < d.rows) e = ld_noise4u(reinterpret_cast<const uint4*>(d.ep + (size_t)u * d.k_rs));
     };
 #ifdef ESTK_TC_PROFILE
     const bool pprof = prof && pwarp == 0;
@@ -538,28 +565,47 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     if (has_cur) {
       describe(cur);
 #pragma unroll
-      for (int u = 0; u < kWin; ++u) load_item(cur, u, T[u], E[u]);
+      for (int u = 0; u < kIU; ++u) load_eps(cur, u, E[u]);
     }
     while (has_cur) {
       bool has_nxt = true;
       for (int sk = 0; sk < kProdGroups && has_nxt; ++sk) has_nxt = advance();
       counter += kProdGroups;
       if (has_nxt) describe(nxt);
+      const uint32_t sa = (2u * cur.kst) % kSlots, sb = (2u * cur.kst + 1u) % kSlots, par = (cur.kst / kSlots) & 1u;
+      const uint32_t base_a = smem_u32(sB + sa * kStageBytes), base_b = smem_u32(sB + sb * kStageBytes);
+      const uint32_t rd = (c8 < 4) ? base_a : base_b;           // this thread's theta chunks live in half A or B
       const long long tw0 = PPROF_T();
-      mbar_wait(smem_u32(bar_empty + cur.stage), cur.phase ^ 1);     // the slot is free (almost always already)
+      mbar_wait(smem_u32(bar_land + sa), par);                  // both theta halves of the stage have landed
       PPROF_ADD(7, tw0);
       const long long tc0 = PPROF_T();
 #pragma unroll
       for (int u = 0; u < kIU; ++u) {
-        form_item(cur, u, T[u % kWin], E[u % kWin]);
-        if (u + kWin < kIU) load_item(cur, u + kWin, T[u % kWin], E[u % kWin]);
-        else if (has_nxt) load_item(nxt, u + kWin - kIU, T[u % kWin], E[u % kWin]);
+        const bool valid = u * kRS + r0 < cur.rows;
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        if (valid) {
+          const float4 ta = ld_shared_v4(rd + roff0 + (uint32_t)u * (kRS * 128));
+          const float4 tb = ld_shared_v4(rd + roff1 + (uint32_t)u * (kRS * 128));
+          const float4 t0 = (c8 < 4) ? ta : tb, t1 = (c8 < 4) ? tb : ta;      // k ascending
+          const uint4 e = E[u];
+          const float2 e0 = unpack_f16(e.x), e1 = unpack_f16(e.y), e2 = unpack_f16(e.z), e3 = unpack_f16(e.w);
+          w0 = pack_f16(fmaf(cur.sg, e0.x, t0.x), fmaf(cur.sg, e0.y, t0.y));
+          w1 = pack_f16(fmaf(cur.sg, e1.x, t0.z), fmaf(cur.sg, e1.y, t0.w));
+          w2 = pack_f16(fmaf(cur.sg, e2.x, t1.x), fmaf(cur.sg, e2.y, t1.y));
+          w3 = pack_f16(fmaf(cur.sg, e3.x, t1.z), fmaf(cur.sg, e3.y, t1.w));
+        }
+        __syncwarp();                         // the row's eight lanes have read half A before one of them overwrites it
+        if (valid) st_shared_v4(base_a + woff + (uint32_t)u * (kRS * 128), w0, w1, w2, w3);
+        if (has_nxt) load_eps(nxt, u, E[u]);  // the noise of this thread's next stage, a whole stage ahead
       }
       PPROF_ADD(8, tc0);
       const long long tf0 = PPROF_T();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_full + cur.stage), 0);
+      if (lane == 0) {
+        mbar_arrive_on<CG>(smem_u32(bar_full + sa), 0);                                          // tile formed (leader's barrier)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_emptyB + sb)) : "memory");   // half B is free
+      }
       PPROF_ADD(9, tf0);
       cur = nxt;
       has_cur = has_nxt;
@@ -574,8 +620,59 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
 }
 
 size_t f16_smem_bytes() {
-  return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)kStages * kStageBytes + 2 * kMaxW * sizeof(float) +
-         (2 * kStages + 4) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + kEpiWarps * sizeof(float) + 64;
+  return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)kSlots * kStageBytes + 2 * kMaxW * sizeof(float) +
+         (4 * kSlots + 4) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + kEpiWarps * sizeof(float) + 64;
+}
+
+// ---- TMA descriptors of the fp32 theta (host side)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int build_theta_maps(const estk_mlp_desc& d, const float* theta, ThetaMaps* out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ESTK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      estk_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return ESTK_ERR_CUDA;
+    }
+    encode = (EncodeTiledFn)fn;
+  }
+  // single-entry cache: the descriptors only depend on theta's address and the layer shapes
+  static thread_local struct { const float* ptr; estk_mlp_desc desc; int device; bool valid; ThetaMaps maps; } cache = {};
+  int dev = -1;
+  ESTK_CUDA(cudaGetDevice(&dev));
+  if (cache.valid && cache.ptr == theta && cache.device == dev && memcmp(&cache.desc, &d, sizeof(d)) == 0) {
+    *out = cache.maps;
+    return ESTK_OK;
+  }
+  memset(out, 0, sizeof(*out));
+  int64_t pb = 0;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const int K = d.dims[l], N = d.dims[l + 1];
+    for (int t = 0; t < 2; ++t) {
+      const int n0 = t * 256;
+      const int Nt = (n0 < N) ? (N - n0 < 256 ? N - n0 : 256) : (N < 256 ? N : 256);   // tile 1 of a one-tile layer: unused copy
+      const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+      const cuuint64_t gstride[1] = {(cuuint64_t)K * 4};
+      const cuuint32_t box[2] = {32u, (cuuint32_t)(Nt / CG)};
+      const cuuint32_t estride[2] = {1, 1};
+      const CUresult r = encode(&out->m[l][t], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(theta + pb), gdim, gstride,
+                                box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        estk_set_error("cuTensorMapEncodeTiled failed (%d) for layer %d tile %d [N=%d K=%d box %dx32]", (int)r, l, t, N, K,
+                       Nt / CG);
+        return ESTK_ERR_CUDA;
+      }
+    }
+    pb += (int64_t)K * N + N;
+  }
+  cache.ptr = theta; cache.desc = d; cache.device = dev; cache.maps = *out; cache.valid = true;
+  return ESTK_OK;
 }
 
 int f16_supported(const estk_mlp_desc& d, int B, const char** why) {
@@ -598,7 +695,7 @@ int run_f16(estk_ctx* ctx, EvalF16Params& p, cudaStream_t stream, const char* wh
     return ESTK_ERR_UNSUPPORTED;
   }
   ESTK_CHECK_ARG(p.pairs >= 1 && p.pairs <= ESTK_MAX_POPULATION / 2, "%s: pairs=%d", who, p.pairs);
-  ESTK_CHECK_ARG((((uintptr_t)p.theta) & 31u) == 0, "%s: theta must be 32-byte aligned (256-bit loads)", who);
+  ESTK_CHECK_ARG((((uintptr_t)p.theta) & 15u) == 0, "%s: theta must be 16-byte aligned (TMA)", who);
   p.chunks = p.B / (128 * CG);
   ESTK_CHECK_ARG(p.chunks * CG <= kEvalMaxChunks, "%s: batch too large", who);
   p.n_centre = p.centre_out ? p.chunks : 0;
@@ -609,6 +706,8 @@ int run_f16(estk_ctx* ctx, EvalF16Params& p, cudaStream_t stream, const char* wh
 #ifdef ESTK_TC_PROFILE
   { const char* e = getenv("ESTK_TC_PROFILE"); p.prof = e ? atoi(e) : 0; }
 #endif
+  static thread_local ThetaMaps maps;
+  { const int rc = build_theta_maps(p.desc, p.theta, &maps); if (rc != ESTK_OK) return rc; }
   const size_t smem = f16_smem_bytes();
   ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int clusters = ctx->sm_count / CG;
@@ -625,7 +724,7 @@ int run_f16(estk_ctx* ctx, EvalF16Params& p, cudaStream_t stream, const char* wh
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_f16_kernel, p));
+  ESTK_CUDA(cudaLaunchKernelEx(&cfg, eval_mlp_f16_kernel, p, maps));
   return ESTK_OK;
 }
 
