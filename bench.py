@@ -257,22 +257,29 @@ def run_ours(args, wl, rank, world, local_rank):
         return sorted(a.elapsed_time(b) for a, b in evs)[iters // 2]
 
     from estorch_b200.backend import adam_desc
-    R = es._returns
+    R = es._returns if world == 1 else es._rm_buffers()[0]
+    gt = es._grad_table()                       # the exact fp16 copy of the table when there is one
+    tbytes = gt.element_size()
+    rp, rm_ = (R[es._pair_begin: es._pair_begin + pl], R[pairs + es._pair_begin: pairs + es._pair_begin + pl]) \
+        if world == 1 else (R[rank, 0], R[rank, 1])
     t_eval = timed(lambda: be.eval_mlp(es._spec.dims, slot.theta, es._table, es._offsets, es._order, pl, sigma,
-                                       es._obs, es._tgt, R[es._pair_begin: es._pair_begin + pl],
-                                       R[pairs + es._pair_begin: pairs + es._pair_begin + pl],
-                                       **es._eval_kw(slot)), iters=3)
+                                       es._obs, es._tgt, rp, rm_, **es._eval_kw(slot)), iters=3)
     scratch = [t.clone() for t in (slot.theta, slot.m, slot.v)]
     ad = adam_desc(lr=0.01)
     if world == 1:
-        t_grad = timed(lambda: be.rank_grad_adam(R, None, 1.0, 0.0, P, es._table, es._offsets, es._order,
-                                                 scratch[0], scratch[1], scratch[2], slot.state, ad,
+        st_scratch = slot.state.clone()
+        t_grad = timed(lambda: be.rank_grad_adam(R, None, 1.0, 0.0, P, gt, es._offsets, es._order,
+                                                 scratch[0], scratch[1], scratch[2], st_scratch, ad,
                                                  es._ranks, None, None))
     else:
-        t_grad = timed(lambda: be.rank_grad(R, None, 1.0, 0.0, P, es._table, es._offsets, es._order,
-                                            es._pair_begin, pl, n, es._grad, es._ranks, None))
-    bytes_grad = 4 * n * pl + 28 * n + 8 * P                       # SURVEY 8d, per launch on this rank
-    bytes_eval = 4 * n * pl + 4 * n + 4 * B * (dims[0] + dims[-1]) + 4 * P
+        rmaj = gt.dtype == torch.float16
+        t_grad = timed(lambda: be.rank_grad(R.view(-1) if rmaj else es._returns, None, 1.0, 0.0, P, gt, es._offsets,
+                                            es._order, es._pair_begin, pl, n, es._grad, es._ranks, None,
+                                            world=world if rmaj else 1))
+    # algorithmic bytes per launch on this rank (SURVEY 8d with the table's element size: the engine's
+    # table entries are fp16-representable and both kernels stream the exact 16-bit copy)
+    bytes_grad = tbytes * n * pl + 28 * n + 8 * P
+    bytes_eval = tbytes * n * pl + 4 * n + 4 * B * (dims[0] + dims[-1]) + 4 * P
     flops_eval = 2.0 * n * B * 2 * pl
     k_grad = {"kernel": "rank_grad_adam" if world == 1 else "rank_grad", "bound": "hbm",
               "achieved": bytes_grad / t_grad / 1e6, "peak": peaks["hbm"], "unit": "GB/s",

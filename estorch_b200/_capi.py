@@ -69,6 +69,9 @@ SIGNATURES = {
     "estk_rank_grad_adam": [_P, _P, _P, _F32, _F32, _I32, _P, _P, _P, _I64, _P, _P, _P, _P,
                             C.POINTER(EstkAdamDesc), _P, _P, _P, _P],
     "estk_rank_grad": [_P, _P, _P, _F32, _F32, _I32, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P, _P],
+    "estk_rank_grad_adam_h": [_P, _P, _P, _F32, _F32, _I32, _P, _P, _P, _I64, _P, _P, _P, _P,
+                              C.POINTER(EstkAdamDesc), _P, _P, _P, _P],
+    "estk_rank_grad_h": [_P, _P, _P, _F32, _F32, _I32, _I32, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P, _P],
     "estk_clamp_adam": [_P, _P, _I32, _I64, _P, _P, _P, _P, C.POINTER(EstkAdamDesc), _P, _P],
     "estk_knn_novelty": [_P, _P, _I32, _P, _I32, _I32, _I32, _P, _P],
 }

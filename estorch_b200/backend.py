@@ -247,15 +247,18 @@ class CudaBackend:
             self._ctx, self._ptr(state, torch.uint8, "state"), self._ptr(reward, torch.float32, "reward"),
             self._ptr(theta, torch.float32, "theta"), self._ptr(best_theta, torch.float32, "best_theta"),
             theta.numel(), self._stream()), "estk_track_best")
-        self.launches += 2
+        self.launches += 1
 
     # ---------------------------------------------------------------- rank + grad + Adam
     def rank_grad_adam(self, returns, novelty, w_rew, w_nov, P, table, offsets, order, theta, m, v,
                        state, adam, ranks_out=None, ranks2_out=None, grad_out=None):
-        _capi.check(self.lib.estk_rank_grad_adam(
+        """``table`` float32, or float16 = the exact 16-bit copy (half the bytes, same result)."""
+        h = table.dtype == torch.float16
+        fn = self.lib.estk_rank_grad_adam_h if h else self.lib.estk_rank_grad_adam
+        _capi.check(fn(
             self._ctx, self._ptr(returns, torch.float32, "returns"),
             self._ptr(novelty, torch.float32, "novelty"), float(w_rew), float(w_nov), int(P),
-            self._ptr(table, torch.float32, "table"), self._ptr(offsets, torch.int64, "offsets"),
+            self._ptr(table, table.dtype if h else torch.float32, "table"), self._ptr(offsets, torch.int64, "offsets"),
             self._ptr(order, torch.int32, "order"), theta.numel(),
             self._ptr(theta, torch.float32, "theta"), self._ptr(m, torch.float32, "m"),
             self._ptr(v, torch.float32, "v"), self._ptr(state, torch.uint8, "state"), C.byref(adam),
@@ -264,15 +267,23 @@ class CudaBackend:
         self.launches += 1
 
     def rank_grad(self, returns, novelty, w_rew, w_nov, P, table, offsets, order, pair_begin,
-                  pairs_local, n, grad_sum_out, ranks_out=None, ranks2_out=None):
-        _capi.check(self.lib.estk_rank_grad(
-            self._ctx, self._ptr(returns, torch.float32, "returns"),
-            self._ptr(novelty, torch.float32, "novelty"), float(w_rew), float(w_nov), int(P),
-            self._ptr(table, torch.float32, "table"), self._ptr(offsets, torch.int64, "offsets"),
-            self._ptr(order, torch.int32, "order"), int(pair_begin), int(pairs_local), int(n),
-            self._ptr(grad_sum_out, torch.float32, "grad_sum_out"),
-            self._ptr(ranks_out, torch.int32, "ranks_out"), self._ptr(ranks2_out, torch.int32, "ranks2_out"),
-            self._stream()), "estk_rank_grad")
+                  pairs_local, n, grad_sum_out, ranks_out=None, ranks2_out=None, world=1):
+        """``table`` float32 (member-order returns only), or float16 = the exact 16-bit copy;
+        with the latter ``world > 1`` declares rank-major returns ``[world][2][pairs/world]``."""
+        tail = (self._ptr(offsets, torch.int64, "offsets"),
+                self._ptr(order, torch.int32, "order"), int(pair_begin), int(pairs_local), int(n),
+                self._ptr(grad_sum_out, torch.float32, "grad_sum_out"),
+                self._ptr(ranks_out, torch.int32, "ranks_out"), self._ptr(ranks2_out, torch.int32, "ranks2_out"),
+                self._stream())
+        head = (self._ctx, self._ptr(returns, torch.float32, "returns"),
+                self._ptr(novelty, torch.float32, "novelty"), float(w_rew), float(w_nov), int(P))
+        if table.dtype == torch.float16:
+            rc = self.lib.estk_rank_grad_h(*head, int(world), self._ptr(table, torch.float16, "table16"), *tail)
+        else:
+            if world != 1:
+                raise ValueError("rank-major returns (world > 1) need the fp16 table entry point")
+            rc = self.lib.estk_rank_grad(*head, self._ptr(table, torch.float32, "table"), *tail)
+        _capi.check(rc, "estk_rank_grad")
         self.launches += 1
 
     def clamp_adam(self, grad_sum, P, theta, m, v, state, adam, grad_out=None):

@@ -70,7 +70,14 @@ constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, la
 constexpr int kProdGroups = ESTK_F16_GROUPS, kProdGroupWarps = kProdWarps / kProdGroups, kPT = 32 * kProdGroupWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 // 128*40 + 256*112 + 256*104 = 60416 <= 640*96 = 61440
-constexpr int kRegsCtl = 40, kRegsEpi = 112, kRegsProd = 104;
+#ifndef ESTK_F16_REGS_EPI
+#define ESTK_F16_REGS_EPI 112
+#endif
+#ifndef ESTK_F16_REGS_PROD
+#define ESTK_F16_REGS_PROD 104
+#endif
+constexpr int kRegsCtl = 40, kRegsEpi = ESTK_F16_REGS_EPI, kRegsProd = ESTK_F16_REGS_PROD;
+static_assert(128 * kRegsCtl + 256 * kRegsEpi + 256 * kRegsProd <= 640 * 96, "register pool of the CTA");
 
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -494,6 +501,10 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // thread index inside the group
     constexpr int kRS = kPT / 8;             // tile rows covered by one item step of the group
     constexpr int kIU = 128 / kRS;           // item steps per (full) stage
+#ifndef ESTK_F16_FB
+#define ESTK_F16_FB 2
+#endif
+    constexpr int kFB = ESTK_F16_FB;         // rows formed per step (ld.shared batch)
     const int r0 = ptid >> 3, c8 = ptid & 7;
     // byte offsets inside a slot of the two 16-byte theta chunks this thread reads (row r0; rows
     // r0 + u*kRS add u*kRS*128: kRS is a multiple of 8, the swizzle term does not change).  The
@@ -579,24 +590,36 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
       mbar_wait(smem_u32(bar_land + sa), par);                  // both theta halves of the stage have landed
       PPROF_ADD(7, tw0);
       const long long tc0 = PPROF_T();
+      // kFB rows per step: all ld.shared of the step first (their latency overlaps), one
+      // __syncwarp, then the in-place stores and the refill of the noise registers
 #pragma unroll
-      for (int u = 0; u < kIU; ++u) {
-        const bool valid = u * kRS + r0 < cur.rows;
-        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-        if (valid) {
-          const float4 ta = ld_shared_v4(rd + roff0 + (uint32_t)u * (kRS * 128));
-          const float4 tb = ld_shared_v4(rd + roff1 + (uint32_t)u * (kRS * 128));
-          const float4 t0 = (c8 < 4) ? ta : tb, t1 = (c8 < 4) ? tb : ta;      // k ascending
-          const uint4 e = E[u];
-          const float2 e0 = unpack_f16(e.x), e1 = unpack_f16(e.y), e2 = unpack_f16(e.z), e3 = unpack_f16(e.w);
-          w0 = pack_f16(fmaf(cur.sg, e0.x, t0.x), fmaf(cur.sg, e0.y, t0.y));
-          w1 = pack_f16(fmaf(cur.sg, e1.x, t0.z), fmaf(cur.sg, e1.y, t0.w));
-          w2 = pack_f16(fmaf(cur.sg, e2.x, t1.x), fmaf(cur.sg, e2.y, t1.y));
-          w3 = pack_f16(fmaf(cur.sg, e3.x, t1.z), fmaf(cur.sg, e3.y, t1.w));
+      for (int ub = 0; ub < kIU; ub += kFB) {
+        float4 ta[kFB], tb[kFB];
+#pragma unroll
+        for (int q = 0; q < kFB; ++q) {
+          if ((ub + q) * kRS + r0 < cur.rows) {
+            ta[q] = ld_shared_v4(rd + roff0 + (uint32_t)(ub + q) * (kRS * 128));
+            tb[q] = ld_shared_v4(rd + roff1 + (uint32_t)(ub + q) * (kRS * 128));
+          }
         }
-        __syncwarp();                         // the row's eight lanes have read half A before one of them overwrites it
-        if (valid) st_shared_v4(base_a + woff + (uint32_t)u * (kRS * 128), w0, w1, w2, w3);
-        if (has_nxt) load_eps(nxt, u, E[u]);  // the noise of this thread's next stage, a whole stage ahead
+        uint32_t w[kFB][4];
+#pragma unroll
+        for (int q = 0; q < kFB; ++q) {
+          const float4 t0 = (c8 < 4) ? ta[q] : tb[q], t1 = (c8 < 4) ? tb[q] : ta[q];      // k ascending
+          const uint4 e = E[ub + q];
+          const float2 e0 = unpack_f16(e.x), e1 = unpack_f16(e.y), e2 = unpack_f16(e.z), e3 = unpack_f16(e.w);
+          w[q][0] = pack_f16(fmaf(cur.sg, e0.x, t0.x), fmaf(cur.sg, e0.y, t0.y));
+          w[q][1] = pack_f16(fmaf(cur.sg, e1.x, t0.z), fmaf(cur.sg, e1.y, t0.w));
+          w[q][2] = pack_f16(fmaf(cur.sg, e2.x, t1.x), fmaf(cur.sg, e2.y, t1.y));
+          w[q][3] = pack_f16(fmaf(cur.sg, e3.x, t1.z), fmaf(cur.sg, e3.y, t1.w));
+        }
+        __syncwarp();                         // every lane has read its rows of half A before any lane overwrites them
+#pragma unroll
+        for (int q = 0; q < kFB; ++q) {
+          if ((ub + q) * kRS + r0 < cur.rows)
+            st_shared_v4(base_a + woff + (uint32_t)(ub + q) * (kRS * 128), w[q][0], w[q][1], w[q][2], w[q][3]);
+          if (has_nxt) load_eps(nxt, ub + q, E[ub + q]);  // the noise of this thread's next stage, a whole stage ahead
+        }
       }
       PPROF_ADD(8, tc0);
       const long long tf0 = PPROF_T();

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(1024) make_offsets_kernel(uint64_t seed, const
                                                             int32_t* __restrict__ order_out,
                                                             int sort_len) {
   extern __shared__ uint64_t keys[];
-  const uint64_t gen = state ? (uint64_t)state->generation : (uint64_t)gen_host;
+  const uint64_t gen = (uint64_t)((state ? state->generation : 0) + gen_host);
   const uint64_t base = estk_mix64(seed ^ (gen * ESTK_GEN_MUL));
   for (int i = threadIdx.x; i < sort_len; i += blockDim.x) {
     uint64_t key = ~0ull;

@@ -235,8 +235,10 @@ class ES:
         size = max(size, n_pad + 32) // 32 * 32
         self._table = self._be.alloc(size)
         self._be.fill_noise_table(self._table, self._noise_seed)
-        self._table16 = None
+        self._table16 = None            # bf16 shadow ("bf16s" only)
         self._table16_version = None
+        self._table_h = None            # EXACT fp16 copy of the table (None while unchecked / not exact)
+        self._table_h_version, self._table_h_ok = None, False
         self._ensure_table16()
 
         # ---- population bookkeeping
@@ -393,7 +395,12 @@ class ES:
         estorch.py:441)."""
         if "_population_returns" in self.__dict__:
             return self.__dict__["_population_returns"]
-        cols = [self._returns] if self._novelty is None else [self._returns, self._novelty]
+        if getattr(self, "_rm_live", False):       # multi-GPU fused runs keep the all-gathered layout
+            cols = [self._member_order(self._returns_rm)]
+            if self._novelty is not None:
+                cols.append(self._member_order(self._novelty_rm))
+        else:
+            cols = [self._returns] if self._novelty is None else [self._returns, self._novelty]
         return torch.stack(cols, dim=1).cpu().numpy()
 
     @population_returns.setter
@@ -444,10 +451,14 @@ class ES:
                 return s
         raise ValueError("policy is not managed by this ES instance")
 
-    def _draw_offsets(self):
+    def _draw_offsets(self, state=None, gen_offset=0):
+        """Offsets (and the offset-sorted order) of this generation's local pairs.  With
+        ``state`` the generation index is read on the device (state.generation +
+        gen_offset == self._generation), so the call can be replayed from a CUDA graph."""
         be = self._be
         self._offsets_gen = self._generation
-        be.make_offsets(self._noise_seed, None, self._generation, self._pair_begin, self._pairs_local,
+        be.make_offsets(self._noise_seed, state, self._generation if state is None else gen_offset,
+                        self._pair_begin, self._pairs_local,
                         self._table.numel(), self.n_parameters, self._offsets, self._order)
         self._offsets_all_gen = self._generation if self.n_workers == 1 else None
 
@@ -480,7 +491,7 @@ class ES:
             self._novelty.copy_(torch.as_tensor(np.ascontiguousarray(novelty, dtype=np.float32)))
             nov = self._novelty
         gsum = self._grad
-        be.rank_grad(self._returns, nov, w_rew, w_nov, P, self._table, self._offsets, self._order,
+        be.rank_grad(self._returns, nov, w_rew, w_nov, P, self._grad_table(), self._offsets, self._order,
                      self._pair_begin, self._pairs_local, self.n_parameters, gsum, self._ranks, self._ranks2)
         self._all_reduce(gsum)
         return gsum / float(P)
@@ -534,6 +545,23 @@ class ES:
             setattr(self, k, v)
         self._host_cache = {}
 
+    # -- rank-major returns: every rank's evaluate kernel writes its (+, -) halves straight into its
+    #    block of a [W, 2, pairs/W] buffer, ONE in-place all-gather completes it, and the rank kernel
+    #    (estk_rank_grad_h, `world`) reads that layout: no staging copies (estorch.py:228-233 Recv loop)
+    def _member_order(self, t_rm):
+        return t_rm.view(self.n_workers, 2, self._pairs_local).permute(1, 0, 2).reshape(-1)
+
+    def _rm_buffers(self):
+        if getattr(self, "_returns_rm", None) is None:
+            self._returns_rm = self._be.zeros(self.n_workers, 2, self._pairs_local)
+            self._novelty_rm = self._be.zeros(self.n_workers, 2, self._pairs_local) \
+                if self._ALGORITHM_TYPE == _Algorithm.novelty else None
+        return self._returns_rm, self._novelty_rm
+
+    def _all_gather_rm(self, t_rm):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(t_rm.view(-1), t_rm[self.rank].reshape(-1))
+
     def _ensure_dist(self):
         if self.n_workers > 1:
             import torch.distributed as dist
@@ -548,28 +576,38 @@ class ES:
         g = optimizer.param_groups[0]
         return adam_desc(lr=g["lr"], betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], clamp=1.0)
 
+    def _exact_table16(self):
+        """The EXACT fp16 copy of the noise table, or None when some entry of the table is
+        not fp16-representable (only tables written from outside: estk_fill_noise_table
+        rounds every entry to fp16).  Consumers convert it back to fp32 exactly, so it is a
+        drop-in for the fp32 table at half the bytes: the tensor-core evaluate streams it
+        and so does the gradient reduction.  Re-checked when the table was overwritten in
+        place (``tensor._version``); one host synchronisation per check (setup time)."""
+        if self._table_h_version != self._table._version:
+            if self._table_h is None:
+                self._table_h = self._be.alloc(self._table.numel(), dtype=torch.float16)
+            self._table_h_ok = self._be.shadow_f16(self._table, self._table_h) == 0
+            self._table_h_version = self._table._version
+        return self._table_h if self._table_h_ok else None
+
+    def _grad_table(self):
+        """Table the gradient reduction reads: the exact fp16 copy when there is one."""
+        t = self._exact_table16() if hasattr(self._be, "shadow_f16") else None
+        return self._table if t is None else t
+
     def _ensure_table16(self):
-        """16-bit copy of the noise table for the tensor-core evaluate modes: ``"f16"``
-        needs the EXACT fp16 copy (the table's entries are fp16-representable by
-        construction, estk_fill_noise_table), ``"bf16s"`` a rounded bf16 shadow.  Rebuilt
-        when the table was overwritten in place (``tensor._version``)."""
-        if self._precision not in ("f16", "bf16s"):
-            return
-        if self._table16 is not None and self._table16_version == self._table._version:
-            return
+        """16-bit table copies of the tensor-core evaluate modes: ``"f16"`` needs the exact
+        fp16 copy, ``"bf16s"`` a rounded bf16 shadow."""
         if self._precision == "f16":
-            if self._table16 is None:
-                self._table16 = self._be.alloc(self._table.numel(), dtype=torch.float16)
-            inexact = self._be.shadow_f16(self._table, self._table16)
-            if inexact:
-                raise ValueError(f"eval_precision='f16' needs a noise table whose entries are exactly "
-                                 f"fp16-representable ({inexact} are not); use the engine's own table or "
-                                 "eval_precision='fp32'")
-        else:
-            if self._table16 is None:
-                self._table16 = self._be.alloc(self._table.numel(), dtype=torch.bfloat16)
-            self._be.shadow_bf16(self._table, self._table16)
-        self._table16_version = self._table._version
+            if self._exact_table16() is None:
+                raise ValueError("eval_precision='f16' needs a noise table whose entries are exactly "
+                                 "fp16-representable; use the engine's own table or eval_precision='fp32'")
+        elif self._precision == "bf16s":
+            if self._table16 is None or self._table16_version != self._table._version:
+                if self._table16 is None:
+                    self._table16 = self._be.alloc(self._table.numel(), dtype=torch.bfloat16)
+                self._be.shadow_bf16(self._table, self._table16)
+                self._table16_version = self._table._version
 
     def _eval_kw(self, slot, centre=False):
         """precision + the 16-bit table copy (and, for "bf16s", a refreshed bf16 shadow of
@@ -582,56 +620,91 @@ class ES:
             kw["theta16"] = slot.theta16
         if self._precision in ("f16", "bf16s") and not centre:
             self._ensure_table16()
-            kw["table16"] = self._table16
+            kw["table16"] = self._table_h if self._precision == "f16" else self._table16
         return kw
 
-    def _upload_batch(self):
+    _streaming = False          # the agent hands a new observation batch to every generation
+    _next_batch = None
+    _next_batch_ptrs = None
+    _peeked = False
+
+    def _peek_batch(self):
+        """Ask the agent for this generation's batch (host side, once per generation)."""
+        if self._peeked:
+            return
+        self._peeked = True
         nb = self.agent.next_batch(self._generation)
+        self._next_batch = nb
+        self._streaming = nb is not None
+        self._next_batch_ptrs = None if nb is None else (nb[0].data_ptr(), nb[1].data_ptr())
         if nb is not None:
             # a deferred post-update rollout belongs to the PREVIOUS batch (estorch.py:181-185
             # runs it before the next generation samples): run it before the buffers change
             self._flush_pending_centre()
+
+    def _upload_batch(self):
+        self._peek_batch()
+        self._peeked = False
+        nb, self._next_batch = self._next_batch, None
+        if nb is not None:
             obs, tgt = nb
             self._obs.copy_(obs, non_blocking=True)
             self._tgt.copy_(tgt, non_blocking=True)
 
     def _fused_generation(self, slot):
-        """One generation, entirely on the device (no host synchronisation)."""
-        be, P, pairs, pl, pb = self._be, self.population_size, self._pairs, self._pairs_local, self._pair_begin
+        """One generation, entirely on the device (no host synchronisation).  The body only
+        enqueues work whose arguments do not depend on host scalars that change from one
+        generation to the next (the generation index and the Adam step live in
+        ``estk_state``), so it can be captured once and replayed as a CUDA graph
+        (``_graphed_generation``)."""
+        be, P, pairs, pl, pb, W = self._be, self.population_size, self._pairs, self._pairs_local, self._pair_begin, \
+            self.n_workers
         dims = None if self._is_conv else self._spec.dims
         self._upload_batch()
         slot.theta_prev.copy_(slot.theta)
-        self._draw_offsets()
-        R = self._returns
+        folded = self._pending_centre
+        self._draw_offsets(slot.state, 1 if folded else 0)
+        gt = self._grad_table()
+        rm = W > 1 and gt.dtype == torch.float16
+        self._rm_live = rm
+        if rm:
+            R = self._rm_buffers()[0]
+            ret_p, ret_m = R[self.rank, 0], R[self.rank, 1]
+        else:
+            R = self._returns
+            ret_p, ret_m = R[pb: pb + pl], R[pairs + pb: pairs + pb + pl]
         if self._is_conv:
             be.eval_conv_vbn(self._spec.n_actions, slot.theta, self._table, self._offsets, self._order, pl,
-                             self.sigma, self._xref, self._obs, self._tgt, R[pb: pb + pl],
-                             R[pairs + pb: pairs + pb + pl], self._conv_scratch)
+                             self.sigma, self._xref, self._obs, self._tgt, ret_p, ret_m, self._conv_scratch)
         else:
             kw = self._eval_kw(slot)
-            folded = self._pending_centre
             if folded:        # the previous generation's post-update rollout rides in this launch
                 kw["centre_out"] = self._episode
             be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
-                        self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl], **kw)
+                        self._obs, self._tgt, ret_p, ret_m, **kw)
             if folded:        # theta is still the previous update's result here (estorch.py:182-185)
                 be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
                 self._pending_centre = False
-        self._all_gather_halves(R)
         ad = self._adam_desc(slot.optimizer)
-        if self.n_workers == 1:
-            be.rank_grad_adam(R, None, 1.0, 0.0, P, self._table, self._offsets, self._order,
+        if W == 1:
+            be.rank_grad_adam(R, None, 1.0, 0.0, P, gt, self._offsets, self._order,
                               slot.theta, slot.m, slot.v, slot.state, ad, self._ranks, None, self._grad)
         else:
-            be.rank_grad(R, None, 1.0, 0.0, P, self._table, self._offsets, self._order, pb, pl,
-                         self.n_parameters, self._grad, self._ranks, None)
+            if rm:
+                self._all_gather_rm(R)
+            else:
+                self._all_gather_halves(R)
+            be.rank_grad(R.view(-1), None, 1.0, 0.0, P, gt, self._offsets, self._order, pb, pl,
+                         self.n_parameters, self._grad, self._ranks, None, world=W if rm else 1)
             self._all_reduce(self._grad)
             be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
         self._best_slot = slot
-        # post-update rollout (estorch.py:181-185).  It is a single 100 us task, so when nobody
-        # can observe it before the next generation (no log() due, not the last generation) it
-        # is deferred and folded into the next generation's evaluate launch.
+        # post-update rollout (estorch.py:181-185).  It is a single 30 us task, so when nobody
+        # can observe it before the next generation (no log() due, not the last generation, the
+        # observation batch does not change) it is deferred and folded into the next generation's
+        # evaluate launch.
         if (self._precision in ("f16", "bf16", "bf16s") and not self._is_conv and not self._stop
+                and not self._streaming
                 and (self.step + 1) % self._log_interval != 0 and self.step + 1 < self.n_steps):
             self._pending_centre = True
             return
@@ -641,6 +714,67 @@ class ES:
         else:
             be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, **self._eval_kw(slot, True))
         be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of a generation
+    def _graph_key(self, slot):
+        """Everything a captured generation bakes in.  None = do not graph this generation."""
+        if (not self._fused or self._dev.type != "cuda" or os.environ.get("ESTORCH_B200_GRAPH", "1") == "0"
+                or getattr(self, "_graph_broken", False) or type(self)._fused_generation is not ES._fused_generation):
+            return None
+        g = slot.optimizer.param_groups[0]
+        will_defer = (self._precision in ("f16", "bf16", "bf16s") and not self._is_conv and not self._stop
+                      and not self._streaming
+                      and (self.step + 1) % self._log_interval != 0 and self.step + 1 < self.n_steps)
+        nb = self._next_batch_ptrs
+        return (id(slot), bool(self._pending_centre), will_defer, float(g["lr"]), tuple(g["betas"]), float(g["eps"]),
+                float(g["weight_decay"]), float(self.sigma), self._table._version, nb,
+                self._obs.data_ptr(), self._tgt.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream)
+
+    def _graphed_generation(self, slot):
+        """Run one fused generation: eagerly the first time a configuration is seen, then
+        captured into a CUDA graph and replayed (one launch instead of ~10 + 2 collectives;
+        at 8 GPUs the host-side launch cost was 40 % of a generation)."""
+        self._peek_batch()
+        key = self._graph_key(slot)
+        if key is None:
+            return self._fused_generation(slot)
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.get(key)
+        if ent is None:                        # first sighting: eager (also warms every lazy allocation)
+            if len(cache) >= 8:                # configurations keep changing (e.g. an lr schedule): stay eager
+                return self._fused_generation(slot)
+            cache[key] = "seen"
+            return self._fused_generation(slot)
+        if ent == "seen":
+            try:
+                graph = torch.cuda.CUDAGraph()
+                launches0 = self._be.launches
+                pending0 = self._pending_centre
+                with torch.cuda.graph(graph, stream=self._graph_stream()):
+                    self._fused_generation(slot)
+                ent = cache[key] = (graph, self._be.launches - launches0, self._pending_centre, self._rm_live)
+                self._pending_centre = pending0
+                self._be.launches = launches0
+            except Exception as e:            # capture is an optimisation: never a reason to stop training
+                self._graph_broken = True
+                cache.pop(key, None)
+                import warnings
+                warnings.warn(f"estorch_b200: CUDA-graph capture of a generation failed ({e!r}); running eagerly")
+                torch.cuda.synchronize(self._dev)
+                return self._fused_generation(slot)
+        graph, n_launches, pending_after, rm_live = ent
+        graph.replay()
+        self._be.launches += n_launches
+        self._pending_centre = pending_after
+        self._rm_live = rm_live
+        self._offsets_gen = self._generation
+        self._offsets_all_gen = self._generation if self.n_workers == 1 else None
+        self._best_slot = slot
+
+    def _graph_stream(self):
+        if getattr(self, "_gstream", None) is None:
+            self._gstream = torch.cuda.Stream(self._dev)
+        return self._gstream
 
     @property
     def population_parameters(self):
@@ -733,7 +867,7 @@ class ES:
                               "_population_returns", "_population_parameters"):
                         self.__dict__.pop(k, None)
                     self._active = self._select_slot()
-                    self._fused_generation(self._active)
+                    self._graphed_generation(self._active)
                 else:
                     self._hooks_generation()
                 if (self.step + 1) % self._log_interval == 0:
@@ -975,28 +1109,43 @@ class NS_ES(ES):
         return self._slots[self.idx]
 
     def _fused_generation(self, slot):
-        be, P, pairs, pl, pb = self._be, self.population_size, self._pairs, self._pairs_local, self._pair_begin
+        be, P, pairs, pl, pb, W = self._be, self.population_size, self._pairs, self._pairs_local, self._pair_begin, \
+            self.n_workers
         dims, ag = self._spec.dims, self.agent
         self._upload_batch()
         slot.theta_prev.copy_(slot.theta)
         self._draw_offsets()
-        R, N, BC = self._returns, self._novelty, self._bc
+        gt = self._grad_table()
+        rm = W > 1 and gt.dtype == torch.float16
+        self._rm_live = rm
+        BC = self._bc
+        if rm:
+            R, N = self._rm_buffers()
+            ret_p, ret_m, nov_p, nov_m = R[self.rank, 0], R[self.rank, 1], N[self.rank, 0], N[self.rank, 1]
+        else:
+            R, N = self._returns, self._novelty
+            ret_p, ret_m = R[pb: pb + pl], R[pairs + pb: pairs + pb + pl]
+            nov_p, nov_m = N[pb: pb + pl], N[pairs + pb: pairs + pb + pl]
         be.eval_mlp(dims, slot.theta, self._table, self._offsets, self._order, pl, self.sigma,
-                    self._obs, self._tgt, R[pb: pb + pl], R[pairs + pb: pairs + pb + pl],
+                    self._obs, self._tgt, ret_p, ret_m,
                     BC[pb: pb + pl], BC[pairs + pb: pairs + pb + pl], ag.bc_obs, ag.bc_dim,
                     **self._eval_kw(slot))
-        be.knn_novelty(BC[pb: pb + pl], self._arch_dev, self.k, N[pb: pb + pl])
-        be.knn_novelty(BC[pairs + pb: pairs + pb + pl], self._arch_dev, self.k, N[pairs + pb: pairs + pb + pl])
-        self._all_gather_halves(R)
-        self._all_gather_halves(N)
+        be.knn_novelty(BC[pb: pb + pl], self._arch_dev, self.k, nov_p)
+        be.knn_novelty(BC[pairs + pb: pairs + pb + pl], self._arch_dev, self.k, nov_m)
         ad = self._adam_desc(slot.optimizer)
         w_rew, w_nov = np.float32(self._w_rew()), np.float32(self._w_nov())
-        if self.n_workers == 1:
-            be.rank_grad_adam(R, N, w_rew, w_nov, P, self._table, self._offsets, self._order,
+        if W == 1:
+            be.rank_grad_adam(R, N, w_rew, w_nov, P, gt, self._offsets, self._order,
                               slot.theta, slot.m, slot.v, slot.state, ad, self._ranks, self._ranks2, self._grad)
         else:
-            be.rank_grad(R, N, w_rew, w_nov, P, self._table, self._offsets, self._order, pb, pl,
-                         self.n_parameters, self._grad, self._ranks, self._ranks2)
+            if rm:
+                self._all_gather_rm(R)
+                self._all_gather_rm(N)
+            else:
+                self._all_gather_halves(R)
+                self._all_gather_halves(N)
+            be.rank_grad(R.view(-1), N.view(-1), w_rew, w_nov, P, gt, self._offsets, self._order, pb, pl,
+                         self.n_parameters, self._grad, self._ranks, self._ranks2, world=W if rm else 1)
             self._all_reduce(self._grad)
             be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
         # _after_optimize (estorch.py:427-432 / :650-662): rollout of the updated

@@ -100,8 +100,10 @@ ESTK_API int estk_fill_noise_table(estk_ctx* ctx, float* table, int64_t len, uin
                           void* stream);
 
 /* offsets_out[i] = 32 * (mix64(mix64(seed ^ gen*C) + pair_begin + i) mod nslots),
- * nslots = (table_len - ceil32(n))/32 + 1.  gen = state->generation when
- * `state` is non-null (device), else gen_host.  order_out (nullable, int32
+ * nslots = (table_len - ceil32(n))/32 + 1.  gen = gen_host, plus state->generation
+ * when `state` is non-null (device counter advanced by estk_track_best: a generation
+ * replayed from a CUDA graph passes a constant gen_host -- 0, or 1 while the previous
+ * generation's estk_track_best is still folded into this one -- and never a host scalar).  order_out (nullable, int32
  * [pairs]) receives the local pair indices sorted by offset (ties by index):
  * evaluating / reducing pairs in that order lets overlapping table rows hit L2. */
 ESTK_API int estk_make_offsets(estk_ctx* ctx, uint64_t seed, const estk_state* state, int64_t gen_host,
@@ -260,6 +262,27 @@ ESTK_API int estk_rank_grad(estk_ctx* ctx, const float* returns, const float* no
                    const float* table, const int64_t* offsets, const int32_t* order,
                    int32_t pair_begin, int32_t pairs_local, int64_t n,
                    float* grad_sum_out, int32_t* ranks_out, int32_t* ranks2_out, void* stream);
+
+/* The same two entry points reading the EXACT 16-bit copy of the table (estk_shadow_f16):
+ * 8 noise values per 128-bit load, half the bytes per pair row, bit-identical results
+ * (every fp16 value converts exactly to the fp32 value the fp32 table holds).
+ * estk_rank_grad_h additionally takes `world`: with world > 1, `returns` / `novelty` are
+ * laid out RANK-MAJOR, [world][2][pairs/world] -- exactly what an in-place all-gather of
+ * each rank's (returns_plus[pairs_local], returns_minus[pairs_local]) block produces, so
+ * no re-ordering copy is needed (member j < pairs of rank r, local index i, sits at
+ * ((2r + 0) * pairs_local + i), its mirror at ((2r + 1) * pairs_local + i)); ranks_out
+ * stays in member order and ties are still broken by member index. */
+ESTK_API int estk_rank_grad_adam_h(estk_ctx* ctx, const float* returns, const float* novelty,
+                          float w_rew, float w_nov, int32_t P,
+                          const uint16_t* table16, const int64_t* offsets, const int32_t* order,
+                          int64_t n, float* theta, float* m, float* v, estk_state* state,
+                          const estk_adam_desc* adam,
+                          int32_t* ranks_out, int32_t* ranks2_out, float* grad_out, void* stream);
+ESTK_API int estk_rank_grad_h(estk_ctx* ctx, const float* returns, const float* novelty,
+                     float w_rew, float w_nov, int32_t P, int32_t world,
+                     const uint16_t* table16, const int64_t* offsets, const int32_t* order,
+                     int32_t pair_begin, int32_t pairs_local, int64_t n,
+                     float* grad_sum_out, int32_t* ranks_out, int32_t* ranks2_out, void* stream);
 
 /* Epilogue on an all-reduced raw sum: g = grad_sum / P, negate, clamp, Adam.
  * theta/m/v NULL with grad_out set = gradient only (for non-Adam optimizers:

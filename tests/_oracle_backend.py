@@ -66,7 +66,7 @@ class OracleBackend:
         table.copy_(torch.from_numpy(orc.philox_normal_table(table.numel(), seed)))
 
     def make_offsets(self, seed, state, gen_host, pair_begin, pairs, table_len, n, offsets_out, order_out=None):
-        gen = int(self._state(state)["generation"][0]) if state is not None else gen_host
+        gen = (int(self._state(state)["generation"][0]) if state is not None else 0) + gen_host
         offs = orc.noise_offsets(seed, gen, pair_begin, pairs, table_len, n)
         offsets_out.copy_(torch.from_numpy(offs))
         if order_out is not None:
@@ -156,7 +156,13 @@ class OracleBackend:
             ranks2_out.copy_(torch.from_numpy(orc.compute_ranks(_np(novelty)).astype(np.int32)))
 
     def rank_grad(self, returns, novelty, w_rew, w_nov, P, table, offsets, order, pair_begin, pairs_local,
-                  n, grad_sum_out, ranks_out=None, ranks2_out=None):
+                  n, grad_sum_out, ranks_out=None, ranks2_out=None, world=1):
+        table = table.float()                   # the exact fp16 copy converts back to the fp32 table
+        if world > 1:                           # rank-major [world][2][pairs/world] -> member order
+            assert table is not None
+            pl = P // 2 // world
+            unperm = lambda t: None if t is None else t.view(world, 2, pl).permute(1, 0, 2).reshape(-1)
+            returns, novelty = unperm(returns), unperm(novelty)
         self._ranks(returns, novelty, ranks_out, ranks2_out)
         grad_sum_out.copy_(torch.from_numpy(self._raw_sum(returns, novelty, w_rew, w_nov, P, table, offsets,
                                                           pair_begin, pairs_local, n)))
@@ -178,6 +184,7 @@ class OracleBackend:
                        adam, ranks_out=None, ranks2_out=None, grad_out=None):
         n = theta.numel()
         tmp = torch.zeros(n)
+        returns = returns.reshape(-1)
         self.rank_grad(returns, novelty, w_rew, w_nov, P, table, offsets, order, 0, P // 2, n, tmp,
                        ranks_out, ranks2_out)
         self.clamp_adam(tmp, P, theta, m, v, state, adam, grad_out)

@@ -61,12 +61,13 @@ def test_make_offsets_bit_exact(be, pairs, n, table_len, pair_begin, gen):
     want = orc.noise_offsets(0xDEADBEEF12345, gen, pair_begin, pairs, table_len, n)
     np.testing.assert_array_equal(offs.cpu().numpy(), want)
     np.testing.assert_array_equal(order.cpu().numpy(), np.argsort(want, kind="stable").astype(np.int32))
-    # generation read from the device-resident state
+    # generation = device-resident counter + host offset (what a CUDA-graph replay uses)
     st = new_state(be.device)
-    write_state(st, generation=gen)
     offs2 = be.alloc(pairs, dtype=torch.int64)
-    be.make_offsets(0xDEADBEEF12345, st, -1, pair_begin, pairs, table_len, n, offs2, None)
-    np.testing.assert_array_equal(offs2.cpu().numpy(), want)
+    for dev_gen, host_off in ((gen, 0), (max(gen - 1, 0), gen - max(gen - 1, 0))):
+        write_state(st, generation=dev_gen)
+        be.make_offsets(0xDEADBEEF12345, st, host_off, pair_begin, pairs, table_len, n, offs2, None)
+        np.testing.assert_array_equal(offs2.cpu().numpy(), want)
 
 
 def test_perturb_rows_bit_exact(be):
