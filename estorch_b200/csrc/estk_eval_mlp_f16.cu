@@ -17,13 +17,14 @@
 //      across layers (8 k-blocks x 16 KB, updated in place);
 //   B  W_s formed ON THE FLY in a ring of five 16 KB slots (each CTA forms its half of the N tile;
 //      the perturbed weights never exist in global memory).  Stage k = one [128 x 64] k-block:
-//      the TMA engine lands the fp32 theta tile as two [128 x 32] halves (SWIZZLE_128B) in slots
-//      A = 2k mod 5 and B = 2k+1 mod 5; the producers read both, add s*sigma*eps (noise through
-//      registers) and write the fp16 tile IN PLACE over half A -- a row of the fp16 tile occupies
-//      exactly the bytes of the same row of half A, and the eight lanes that own a row sit in one
-//      warp, so a __syncwarp separates the reads from the write.  Slot B is released at once, slot
-//      A by the MMA's commit.  Up to ~64 KB of theta are in flight per SM without holding a single
-//      register (measured: the L2 path needs ~1 KB in flight per GB/s and SM);
+//      the TMA engine lands the fp32 theta tile as two [128 x 32] halves (SWIZZLE_128B), half A in
+//      slot k mod 3 and half B in slot 3 + k mod 2; the producers read both, add s*sigma*eps (noise
+//      through registers) and write the fp16 tile IN PLACE over half A -- a row of the fp16 tile
+//      occupies exactly the bytes of the same row of half A, and the eight lanes that own a row sit
+//      in one warp, so a __syncwarp separates the reads from the write.  A B slot is released by the
+//      producers at once (the next-but-one stage's theta can land while the tile waits for the
+//      MMAs), an A slot by the MMAs' commit.  Up to ~64 KB of theta are in flight per SM without
+//      holding a single register (measured: the L2 path needs ~1 KB in flight per GB/s and SM);
 //   D  the whole layer output [128 x <=512] fp32 in TMEM (512 columns) as two N tiles.
 // Warp roles (20 warps, homogeneous warpgroups so that setmaxnreg can move registers):
 //   WG0    w0 MMA issuer (leader CTA), w1 TMEM allocator + theta TMA thread, w2-3 idle -> 40 registers
@@ -55,7 +56,12 @@ __device__ unsigned long long g_f16_prof[32];   // per-role cycle counters of CT
 namespace {
 
 constexpr int CG = 2;                         // CTAs per cluster = tcgen05 cta_group
-constexpr int kSlots = 5;                     // 16 KB slots of the B ring (beside 128 KB of activations)
+constexpr int kSlots = 5;                     // 16 KB slots of the B ring (beside 128 KB of activations):
+constexpr int kASlots = 3, kBSlots = 2;       // three hold half A / the fp16 tile, two only ever half B
+__host__ __device__ constexpr uint32_t slot_a(uint32_t k) { return k % kASlots; }
+__host__ __device__ constexpr uint32_t slot_b(uint32_t k) { return kASlots + k % kBSlots; }
+__host__ __device__ constexpr uint32_t par_a(uint32_t k) { return (k / kASlots) & 1u; }   // phase of the A slot's k-th use
+__host__ __device__ constexpr uint32_t par_b(uint32_t k) { return (k / kBSlots) & 1u; }
 constexpr int kStages = kSlots;
 constexpr int kStageBytes = kKBlockBytes;
 // TMA descriptors of the fp32 theta, one per (layer, N tile): [N x K] row-major, box [rows of the
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
   uint8_t* sB = sH + (kMaxW / kBlockK) * kKBlockBytes;   // ring
   float* sBias = reinterpret_cast<float*>(sB + kStages * kStageBytes);   // [2][512]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * kMaxW);
-  // per slot: what it holds alternates between "half A" (theta k 0..31, then the fp16 tile) and "half B"
+  // slots 0..2 hold half A of a stage (theta k 0..31), then its fp16 tile; slots 3..4 only ever half B
   uint64_t* bar_full = bars;                   // [kSlots]  fp16 tile formed in the slot           (leader's are used)
   uint64_t* bar_emptyA = bars + kSlots;        // [kSlots]  tile consumed by the MMAs (tcgen05.commit) (local)
   uint64_t* bar_emptyB = bars + 2 * kSlots;    // [kSlots]  half B read by the producers            (local)
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
                 tc_fence_after();
                 second_half_ready = true;
               }
-              const uint32_t stage = (2u * kst) % kSlots, ring_phase = (kst / kSlots) & 1u;   // the stage's A slot
+              const uint32_t stage = slot_a(kst), ring_phase = par_a(kst);   // the stage's A slot
               const long long tf0 = PROF_T();
               mbar_wait(smem_u32(bar_full + stage), ring_phase);
               PROF_ADD(2, tf0);
@@ -246,9 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
       PROF_ADD(0, tm0);
     } else if (warp == 1 && lane == 0) {
       // =================================================================== theta TMA thread
-      // Walks the same (task, layer, n-tile, k-block) stage sequence as the producers; stage k gets
-      // slots A = 2k mod 5 and B = 2k+1 mod 5.  The last use of A was the B half of stage k-3 (freed by
-      // the producers), the last use of B the fp16 tile of stage k-2 (freed by the MMAs' commit).
+      // Walks the same (task, layer, n-tile, k-block) stage sequence as the producers.  Stage k lands
+      // in A slot k mod 3 (last used by stage k-3, freed by the MMAs' commit) and B slot 3 + k mod 2
+      // (last used by stage k-2, freed by the producers as soon as they have read it).
       uint32_t k = 0;
       for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
         for (int l = 0; l < L; ++l) {
@@ -257,9 +263,9 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
             const int rows = min(256, N - n0) / CG;
             const CUtensorMap* map = &maps.m[l][n0 ? 1 : 0];
             for (int kb = 0; kb < K / kBlockK; ++kb, ++k) {
-              const uint32_t sa = (2u * k) % kSlots, sb = (2u * k + 1u) % kSlots;
-              if (k >= 3) mbar_wait(smem_u32(bar_emptyB + sa), ((k - 3) / kSlots) & 1u);
-              if (k >= 2) mbar_wait(smem_u32(bar_emptyA + sb), ((k - 2) / kSlots) & 1u);
+              const uint32_t sa = slot_a(k), sb = slot_b(k);
+              if (k >= kASlots) mbar_wait(smem_u32(bar_emptyA + sa), par_a(k - kASlots));
+              if (k >= kBSlots) mbar_wait(smem_u32(bar_emptyB + sb), par_b(k - kBSlots));
               const uint32_t land = smem_u32(bar_land + sa);
               mbar_arrive_expect_tx(land, (uint32_t)rows * 256u);
               tma_load_2d(smem_u32(sB + sa * kStageBytes), map, kb * kBlockK, n0 + (int)cta_rank * rows, land);
@@ -583,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
       for (int sk = 0; sk < kProdGroups && has_nxt; ++sk) has_nxt = advance();
       counter += kProdGroups;
       if (has_nxt) describe(nxt);
-      const uint32_t sa = (2u * cur.kst) % kSlots, sb = (2u * cur.kst + 1u) % kSlots, par = (cur.kst / kSlots) & 1u;
+      const uint32_t sa = slot_a(cur.kst), sb = slot_b(cur.kst), par = par_a(cur.kst);
       const uint32_t base_a = smem_u32(sB + sa * kStageBytes), base_b = smem_u32(sB + sb * kStageBytes);
       const uint32_t rd = (c8 < 4) ? base_a : base_b;           // this thread's theta chunks live in half A or B
       const long long tw0 = PPROF_T();

@@ -29,6 +29,45 @@ def main():
                  returns=es.population_returns, world=es.n_workers, pairs_local=es._pairs_local,
                  pair_begin=es._pair_begin, episode=es.episode_reward, best_reward=es.best_reward)
         return
+    if algo in ("es_unsynced", "nsra_unsynced", "ns_hooks_unsynced"):
+        # Every rank seeds torch / numpy DIFFERENTLY and nothing preloads theta: what a user's script
+        # does under torchrun.  The reference keeps one master copy (estorch.py:136, :401-408, :444-456);
+        # here rank 0's construction-time state must win on every rank.
+        rank = int(os.environ["RANK"])
+        torch.manual_seed(1000 + rank)
+        np.random.seed(77 + rank)
+        dims = [4, 16, 2]
+        gg = torch.Generator().manual_seed(5)
+        obs, tgt = torch.randn(32, 4, generator=gg), torch.randn(32, 2, generator=gg)
+        common = dict(population_size=16, sigma=0.05, policy_kwargs={"dims": dims}, optimizer_kwargs={"lr": 0.01},
+                      noise_table_size=1 << 12, noise_seed=3, _backend=OracleBackend())
+        if algo == "es_unsynced":
+            es = E.ES(MLP, E.DeviceAgent, torch.optim.Adam, agent_kwargs=dict(obs=obs, target=tgt), **common)
+        elif algo == "nsra_unsynced":
+            es = E.NSRA_ES(MLP, E.DeviceAgent, torch.optim.Adam, weight_t=1,
+                           agent_kwargs=dict(obs=obs, target=tgt, bc_obs=8, bc_dim=16), **common)
+        else:
+            class Noisy:                      # a host agent whose rollouts differ from rank to rank
+                def __init__(self):
+                    self.rng = np.random.RandomState(500 + rank)
+
+                def rollout(self, policy):
+                    with torch.no_grad():
+                        out = policy(obs)
+                    r = float(-((out - tgt) ** 2).mean()) + 1e-3 * float(self.rng.randn())
+                    return r, out[:8].flatten()[:16].numpy().copy() + 1e-3 * self.rng.randn(16).astype(np.float32)
+            es = E.NS_ES(MLP, Noisy, torch.optim.Adam, **common)
+            assert not es._fused
+        es.log = lambda: None
+        es.train(n_steps=3)
+        mods = [es.policy] if algo == "es_unsynced" else [p for p, _ in es.meta_population]
+        theta = np.stack([torch.nn.utils.parameters_to_vector(m.parameters()).detach().numpy() for m in mods])
+        extra = {}
+        if algo != "es_unsynced":
+            extra = dict(archive=np.stack(es._archive), idx=int(es.idx), best=float(es.best_reward))
+        np.savez(os.path.join(out_dir, f"rank{es.rank}.npz"), theta=theta, step=es.step,
+                 returns=es.population_returns, episode=float(es.episode_reward), **extra)
+        return
     g = np.load(os.path.join(ROOT, "tests", "golden",
                              "es_cartpole_p64.npz" if algo == "es" else "nsra_bipedal_p32.npz"))
     dims = [int(d) for d in g["dims"]]

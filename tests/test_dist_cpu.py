@@ -71,3 +71,20 @@ def test_world2_folded_post_update_rollout(tmp_path):
     es.train(n_steps=5)
     assert rel_err(r0["theta"], es._slots[0].theta.numpy()) < 1e-5
     assert abs(float(r0["episode"]) - es.episode_reward) < 1e-5 * abs(es.episode_reward)
+
+
+@pytest.mark.parametrize("algo", ["es_unsynced", "nsra_unsynced", "ns_hooks_unsynced"])
+def test_world2_replicas_agree_without_preloaded_parameters(tmp_path, algo):
+    """Each rank builds its own policy / meta-population from a different torch seed (and, for the
+    hooks-mode NS run, has a host agent with rank-dependent noise and its own numpy RNG): rank 0's
+    state is broadcast before the loop and only rank 0 selects the meta-policy / feeds the archive,
+    as the reference's single master does (estorch.py:136, :401-408, :444-456, :458-471)."""
+    r0, r1 = _run(2, algo, tmp_path)
+    assert int(r0["step"]) == 3 and int(r1["step"]) == 3
+    np.testing.assert_array_equal(r0["theta"], r1["theta"])
+    if algo != "es_unsynced":
+        np.testing.assert_array_equal(r0["archive"], r1["archive"])
+        assert int(r0["idx"]) == int(r1["idx"]) and float(r0["best"]) == float(r1["best"])
+    if algo != "ns_hooks_unsynced":          # device agents are deterministic: identical returns everywhere
+        np.testing.assert_array_equal(r0["returns"], r1["returns"])
+        assert float(r0["episode"]) == float(r1["episode"])
