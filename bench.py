@@ -1,24 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- generations/sec of the ES hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one ES generation (estorch.py:214-248): evaluate the P = 4096
-mirrored members of the 1M-parameter MLP over a synthetic observation batch,
-centred-rank the returns, reduce sum_j w_j * noise_j, negate/clamp, Adam,
-post-update rollout.  Prints ONE JSON line on rank 0.
+A "step" is one ES generation (estorch.py:214-248): evaluate the P = 4096 mirrored members of the
+1M-parameter MLP over a synthetic observation batch, centred-rank the returns, reduce
+sum_j w_j * noise_j, negate/clamp, Adam, post-update rollout.  Prints ONE JSON line on rank 0.
 
-  value  device-resident throughput: inputs already in HBM, no host
-         synchronisation inside the timed region (CUDA events, max over ranks)
-  e2e    the same through the public API with HOST buffers: every generation
-         uploads the observation/target batch from pinned host memory and reads
-         population_returns + episode_reward back (host clock around K steps)
+  value  device-resident throughput: inputs already in HBM, no host synchronisation inside the
+         timed region (CUDA events, max over ranks); log() is not due inside the region
+  e2e    the same through the public API with HOST buffers: every generation uploads the
+         observation/target batch from pinned host memory, calls log() and reads
+         population_returns + episode_reward back (host clock around K steps) -- the headline
   roofline / kernels   per-kernel achieved rate vs MEASURED_PEAKS.json
-  cpu_baseline         the reference's CPU algorithm (oracle/reference_port.py)
-                       on this box's host cores, bounded sample, rank 0 / N=1
+  cpu_baseline         the reference's CPU path on this box's host cores, bounded sample, rank 0 / N=1
+  extra                the other BASELINE.json configs through the same public API (short runs)
 
-`--impl reference` runs only the CPU port (rank 0), same metric/config.
+`--impl reference` runs only the reference's CPU path (rank 0): the UNMODIFIED reference package from
+baseline/_ref (installed by __graft_entry__.build()) when present, else the CPU port of its cost
+structure (oracle/reference_port.py); same metric/config.
 """
 import argparse
 import json
@@ -34,12 +35,21 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+MLP_1M = [128, 512, 512, 512, 512, 288]
 WORKLOADS = {
     # BASELINE.json metric: pop=4096, 1M-param MLP (obs 128, 4x512 hidden, 288 out)
-    "north_star": dict(dims=[128, 512, 512, 512, 512, 288], population_size=4096, sigma=0.02, batch=256),
-    # configs[1]: CartPole-shape 2x64 MLP, pop 4096
-    "cartpole": dict(dims=[4, 64, 64, 2], population_size=4096, sigma=0.1, batch=256),
+    "north_star": dict(algo="es", dims=MLP_1M, population_size=4096, sigma=0.02, batch=256),
+    # configs[1]: CartPole-shape 2x64 MLP, pop 4096, 1 GPU
+    "cartpole": dict(algo="es", dims=[4, 64, 64, 2], population_size=4096, sigma=0.1, batch=256),
+    # configs[2]: the 1M MLP at pop=8192, sigma=0.02, sharded over 8 GPUs (runs on however many there are)
+    "config3": dict(algo="es", dims=MLP_1M, population_size=8192, sigma=0.02, batch=256),
+    # configs[3]: NSRA-ES, BipedalWalker-shape MLP 24->4, pop 2048 (examples/nsra_es.py:61-67)
+    "nsra_bipedal": dict(algo="nsra", dims=[24, 64, 64, 4], population_size=2048, sigma=0.02, batch=256,
+                         bc_obs=64, bc_dim=256),
+    # configs[4]: Atari conv policy 84x84x4 + VirtualBatchNorm, pop 1024 (examples/atari.py:14-37)
+    "atari_vbn": dict(algo="es", conv=True, population_size=1024, sigma=0.02, batch=32, ref_batch=128, n_actions=4),
 }
+METRIC = "generations/sec at pop=4096, 1M-param MLP"
 
 
 class MLP(torch.nn.Module):
@@ -56,7 +66,10 @@ class MLP(torch.nn.Module):
         return self.net(x)
 
 
-def n_params(dims):
+def n_params(wl):
+    if wl.get("conv"):
+        return 677268 if wl["n_actions"] == 4 else None
+    dims = wl["dims"]
     return sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1))
 
 
@@ -113,36 +126,67 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+def _host_threads():
+    """torchrun exports OMP_NUM_THREADS=1: give the CPU arm the cores it would have on its own."""
+    n = max(1, min(os.cpu_count() or 1, 64))
+    torch.set_num_threads(n)
+    return n
+
+
 def cpu_reference(wl, steps, warmup, budget_s=20.0):
-    """Time the reference's CPU algorithm on a bounded population sample and scale
-    linearly in P (sample, cat, rollouts, mm are all O(P*n))."""
+    """Time the reference's CPU path for the workload on a bounded population sample and scale
+    linearly in P (sample, cat, rollouts, mm are all O(P*n)).  Uses the unmodified
+    reference (baseline/_ref) when it is installed, else the CPU port of its cost structure."""
+    from oracle.ref_shim import import_reference
     from oracle.reference_port import time_reference
     from estorch_b200.agents import DeviceAgent
+    cores = _host_threads()
     dims, P, sigma = wl["dims"], wl["population_size"], wl["sigma"]
     obs, tgt = synthetic_batch(dims, wl["batch"])
-    agent = DeviceAgent(obs, tgt)
+    ref = import_reference()
     torch.manual_seed(0)
+
+    def run(sample_P, k, w):
+        if ref is None:
+            return time_reference(MLP, {"dims": dims}, DeviceAgent(obs, tgt), sample_P, sigma, steps=k, warmup=w)
+        # the reference's own classes and loop: ES.__init__ (estorch.py:121-148) + ES.train(n_steps, n_proc=1)
+
+        class Quiet(ref.ES):
+            def log(self):
+                pass
+        es = Quiet(MLP, DeviceAgent, torch.optim.Adam, population_size=sample_P, sigma=sigma,
+                   policy_kwargs={"dims": dims}, agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01})
+        if w:
+            es.train(w)
+        t0 = time.perf_counter()
+        es.train(k)
+        return (time.perf_counter() - t0) / k, {}
+
     probe_P = 16
-    dt, _ = time_reference(MLP, {"dims": dims}, agent, probe_P, sigma, steps=1)
+    dt, _ = run(probe_P, 1, 0)
     per_member = dt / probe_P
     sample_P = int(min(P, max(16, budget_s / max(1, steps + warmup) / per_member)))
     sample_P -= sample_P % 2
-    dt, phases = time_reference(MLP, {"dims": dims}, agent, sample_P, sigma, steps=steps, warmup=warmup)
+    dt, phases = run(sample_P, steps, warmup)
     scale = P / sample_P
     return dict(seconds_per_generation_full=dt * scale, value=1.0 / (dt * scale), sample_P=sample_P,
-                seconds_per_generation_sample=dt, phases_sample_s=phases, cores=torch.get_num_threads())
+                extrapolation_factor=scale, seconds_per_generation_sample=dt, phases_sample_s=phases, cores=cores,
+                kind="port" if ref is None else "reference")
 
 
 def run_reference_arm(args, wl, rank, world):
     if rank != 0:
         return
     r = cpu_reference(wl, args.steps, min(args.warmup, 1), budget_s=60.0)
-    cb = {"value": r["value"], "unit": "generations/s", "cores": r["cores"], "kind": "port",
-          "sample": f"population_size={r['sample_P']} of {wl['population_size']} per step, same policy/batch; "
-                    f"time scaled linearly in P (all phases are O(P*n)); 1 process, {r['cores']} torch threads "
-                    f"of {os.cpu_count()} cpus; phases(s/sample-step)="
-                    f"{ {k: round(v, 4) for k, v in r['phases_sample_s'].items()} }"}
-    line = {"impl": "reference", "metric": "generations/sec at pop=4096, 1M-param MLP", "value": r["value"],
+    what = ("the UNMODIFIED reference package (baseline/_ref, estorch.ES.train(n_proc=1) through a one-rank mpi4py shim)"
+            if r["kind"] == "reference" else "CPU port of the reference's cost structure (oracle/reference_port.py)")
+    cb = {"value": r["value"], "unit": "generations/s", "cores": r["cores"], "kind": r["kind"],
+          "sample_P": r["sample_P"], "extrapolation_factor": r["extrapolation_factor"],
+          "sample": f"{what}; population_size={r['sample_P']} of {wl['population_size']} per step, same policy/batch, "
+                    f"the agent is this repo's DeviceAgent (plain torch rollout: it implements the reference's Agent "
+                    f"protocol); time scaled linearly in P by {r['extrapolation_factor']:.1f} (all phases are O(P*n)); "
+                    f"1 process, {r['cores']} torch threads of {os.cpu_count()} cpus"}
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"],
             "unit": "generations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r["seconds_per_generation_full"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -152,40 +196,42 @@ def run_reference_arm(args, wl, rank, world):
     emit(line)
 
 
-def workload_config(args, wl, world):
-    return {"workload": f"{args.workload}: ES generation, population_size={wl['population_size']} "
-                        f"({wl['population_size'] // 2} antithetic pairs), MLP {wl['dims']} "
-                        f"(n={n_params(wl['dims'])}), synthetic obs batch B={wl['batch']}, sigma={wl['sigma']}, "
-                        f"Adam lr=0.01, noise table 2^{args.table_log2} fp32",
-            "population_size": wl["population_size"], "n_parameters": n_params(wl["dims"]),
+def workload_config(args, wl, world, name=None):
+    name = name or args.workload
+    if wl.get("conv"):
+        shape = (f"conv 4->16 k8 s4 / VirtualBatchNorm / conv 16->32 k4 s2 / VirtualBatchNorm / fc 2592->256->{wl['n_actions']}"
+                 f" (n={n_params(wl)}), {wl['ref_batch']} reference frames")
+    else:
+        shape = f"MLP {wl['dims']} (n={n_params(wl)})"
+    return {"workload": f"{name}: {wl['algo'].upper()} generation, population_size={wl['population_size']} "
+                        f"({wl['population_size'] // 2} antithetic pairs), {shape}, synthetic obs batch "
+                        f"B={wl['batch']}, sigma={wl['sigma']}, Adam lr=0.01, noise table 2^{args.table_log2} entries "
+                        f"(fp32 values with an 11-bit significand; evaluate and reduction stream the exact 16-bit copy)",
+            "population_size": wl["population_size"], "n_parameters": n_params(wl),
             "batch": wl["batch"], "parallelism": f"pairs sharded over {world} GPU(s)",
-            "l2": "noise stream per step (>= 8 GB at north_star) exceeds L2; no flush needed"}
+            "l2": "noise stream per step (>= 4 GB at north_star) exceeds L2; no flush needed"}
 
 
 # ----------------------------------------------------------------------------- our arm
-def run_ours(args, wl, rank, world, local_rank):
-    import torch.distributed as dist
-    from estorch_b200 import ES, DeviceAgent
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
-    dims, P, sigma, B = wl["dims"], wl["population_size"], wl["sigma"], wl["batch"]
-    n, pairs = n_params(dims), P // 2
-    obs, tgt = synthetic_batch(dims, B)
+def build_es(wl, args, eval_precision, log_interval):
+    """The workload through the public API (estorch_b200.ES / NSRA_ES)."""
+    import estorch_b200 as E
+    P, sigma, B = wl["population_size"], wl["sigma"], wl["batch"]
 
-    class Streaming(DeviceAgent):
+    class Streaming(E.DeviceAgent):
         """e2e: each generation's batch comes from pinned host memory."""
         stream_from_host = False
 
-        def __init__(self, obs, target):
-            super().__init__(obs, target)
+        def __init__(self, obs, target, **kw):
+            super().__init__(obs, target, **kw)
             self.h_obs, self.h_tgt = self.obs.clone().pin_memory(), self.target.clone().pin_memory()
 
         def next_batch(self, step):
             return (self.h_obs, self.h_tgt) if self.stream_from_host else None
 
-    class Bench(ES):
+    base = E.NSRA_ES if wl["algo"] == "nsra" else E.ES
+
+    class Bench(base):
         read_back = False
 
         def log(self):
@@ -193,58 +239,163 @@ def run_ours(args, wl, rank, world, local_rank):
                 self.last = (self.population_returns, self.episode_reward)
 
     torch.manual_seed(0)
-    es = Bench(MLP, Streaming, torch.optim.Adam, population_size=P, sigma=sigma,
-               policy_kwargs={"dims": dims}, agent_kwargs=dict(obs=obs, target=tgt),
-               optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << args.table_log2, noise_seed=42,
-               log_interval=10 ** 9, eval_precision=args.eval_precision)
+    common = dict(population_size=P, sigma=sigma, optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << args.table_log2,
+                  noise_seed=42, log_interval=log_interval)
+    if wl.get("conv"):
+        from estorch_b200.vbn import VirtualBatchNorm
+
+        class AtariPolicy(torch.nn.Module):          # architecture of the reference's examples/atari.py:14-37
+            def __init__(self, n_actions, xref):
+                super().__init__()
+                self.xref = xref
+                self.conv1 = torch.nn.Conv2d(4, 16, 8, 4)
+                self.bn1 = VirtualBatchNorm(16)
+                self.conv2 = torch.nn.Conv2d(16, 32, 4, 2)
+                self.bn2 = VirtualBatchNorm(32)
+                self.fc1 = torch.nn.Linear(2592, 256)
+                self.fc2 = torch.nn.Linear(256, n_actions)
+
+            def forward(self, x):
+                F = torch.nn.functional
+                r = F.relu(self.bn1(self.conv1(self.xref.to(x.device))))
+                r = F.relu(self.bn2(self.conv2(r)))
+                x = F.relu(self.bn1(self.conv1(x)))
+                x = F.relu(self.bn2(self.conv2(x)))
+                return self.fc2(F.relu(self.fc1(x.view(-1, 2592))))
+        g = torch.Generator().manual_seed(1234)
+        xref = torch.rand(wl["ref_batch"], 4, 84, 84, generator=g)
+        obs, tgt = torch.rand(B, 4, 84, 84, generator=g), torch.randn(B, wl["n_actions"], generator=g)
+        es = Bench(AtariPolicy, Streaming, torch.optim.Adam, policy_kwargs=dict(n_actions=wl["n_actions"], xref=xref),
+                   agent_kwargs=dict(obs=obs, target=tgt), **common)
+    else:
+        obs, tgt = synthetic_batch(wl["dims"], B)
+        akw = dict(obs=obs, target=tgt)
+        if wl["algo"] == "nsra":
+            akw.update(bc_obs=wl["bc_obs"], bc_dim=wl["bc_dim"])
+        es = Bench(MLP, Streaming, torch.optim.Adam, policy_kwargs={"dims": wl["dims"]}, agent_kwargs=akw,
+                   eval_precision=eval_precision, **common)
     assert es._fused, "bench: fused device path is not active"
-    be = es._be
+    return es, obs, tgt
+
+
+def timed_region(es, steps, warmup, world, dev, sampler=None):
+    """(ms, wall s, clocks, launches) of `steps` generations: CUDA events around the region,
+    barrier + synchronize on both sides, max over ranks."""
+    import torch.distributed as dist
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- value: device-resident, no host sync in the loop
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~1 s to start streaming
-    es.train(args.warmup)
+    es.train(warmup)
     barrier()
-    launches0 = be.launches
+    launches0 = es._be.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
-    es.train(args.steps)
+    es.train(steps)
     ev1.record()
     barrier()
     t1 = time.perf_counter()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = be.launches - launches0
-    clocks = sampler.window(t0, t1) if sampler else None
+    ms, wall = ev0.elapsed_time(ev1), t1 - t0
+    if world > 1:
+        t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall = float(t[0].item()), float(t[1].item())
+    return ms, wall, (sampler.window(t0, t1) if sampler else None), es._be.launches - launches0
 
-    # ---- e2e: host buffers in, host results out, every generation
+
+def run_extra(name, args, world, dev, steps=20):
+    """One of the other BASELINE configs through the same public API: device-resident generations/s
+    and the host-in / host-out e2e figure (short run)."""
+    wl = WORKLOADS[name]
+    try:
+        es, obs, tgt = build_es(wl, args, "auto", 10 ** 9)
+        ms, _, _, launches = timed_region(es, steps, 3, world, dev)
+        es.agent.stream_from_host, es.read_back, es._log_interval = True, True, 1
+        _, wall, _, _ = timed_region(es, steps, 2, world, dev)
+        out = {"config": workload_config(args, wl, world, name)["workload"], "n_gpus": world, "steps": steps,
+               "value": steps / (ms / 1e3), "e2e": steps / wall, "unit": "generations/s",
+               "ms_per_step": ms / steps, "eval_precision": es._precision, "gpu_launches": launches}
+        del es
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:           # an extra must never cost the headline line
+        return {"config": name, "error": repr(e)[:300]}
+
+
+def run_ours(args, wl, rank, world, local_rank):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    P = wl["population_size"]
+    es, obs, tgt = build_es(wl, args, args.eval_precision, 10 ** 9)
+
+    # ---- value: device-resident, no host sync in the loop
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~1 s to start streaming
+    ms, _, clocks, launches = timed_region(es, args.steps, args.warmup, world, dev, sampler)
+
+    # ---- e2e: host buffers in, log() + host results out, every generation
     es.agent.stream_from_host, es.read_back, es._log_interval = True, True, 1
-    es.train(min(args.warmup, 3))
-    barrier()
-    t0 = time.perf_counter()
-    es.train(args.steps)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    _, e2e_s, _, _ = timed_region(es, args.steps, min(args.warmup, 3), world, dev)
     if sampler:
         sampler.stop()
 
+    peaks = load_peaks()
+    kern = {}
+    if not wl.get("conv") and wl["algo"] == "es":
+        kern = kernel_rooflines(es, wl, args, world, rank, peaks)
+    precision, graphed = es._precision, bool(es.__dict__.get("_graphs"))
+    del es
+    torch.cuda.empty_cache()
+
+    extras = None
+    if not args.no_extras and args.workload == "north_star":
+        extras = {}
+        for name in ("cartpole", "nsra_bipedal", "config3", "atari_vbn"):
+            extras[name] = run_extra(name, args, world, dev, steps=5 if name == "atari_vbn" else 20)
+
     if rank != 0:
         return
-    peaks = load_peaks()
-    # ---- per-kernel device time (CUDA events on the launching stream), N=1 geometry of this rank
-    pl = es._pairs_local
-    slot = es._slots[0]
+    line = {"metric": METRIC, "value": args.steps / (ms / 1e3),
+            "unit": "generations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": {"f16": "f32 (fp32-equivalent: evaluate GEMMs on tcgen05 with fp16 operands = 11-bit significand, "
+                             "TF32 class, each weight formed in fp32 from fp32 theta + the exactly-16-bit noise value and "
+                             "rounded once, f32 accumulate, f32 bias/loss; f32 ranks, reduction, Adam)",
+                      "bf16": "bf16 operands / f32 accumulate (evaluate GEMMs); f32 noise, ranks, reduction, Adam",
+                      "bf16s": "bf16 operands formed from bf16 shadows of theta/noise, f32 accumulate (evaluate "
+                               "GEMMs); f32 noise table, ranks, reduction, Adam"}.get(precision, "f32"),
+            "eval_precision": precision,
+            "data": "synthetic", "config": workload_config(args, wl, world),
+            "e2e": {"value": args.steps / e2e_s, "unit": "generations/s",
+                    "h2d_bytes_per_step": int(obs.numel() * 4 + tgt.numel() * 4),
+                    "d2h_bytes_per_step": int(4 * P + 32)},
+            "gpu_launches": launches, "cuda_graph": graphed, "clocks": clocks}
+    line.update(kern)
+    line["cpu_baseline"] = None
+    if world == 1 and not args.no_cpu_baseline and not wl.get("conv") and wl["algo"] == "es":
+        r = cpu_reference(wl, steps=1, warmup=0, budget_s=15.0)
+        line["cpu_baseline"] = {
+            "value": r["value"], "unit": "generations/s", "cores": r["cores"], "kind": r["kind"],
+            "sample_P": r["sample_P"], "extrapolation_factor": r["extrapolation_factor"],
+            "sample": f"1 generation of {'the unmodified reference (baseline/_ref)' if r['kind'] == 'reference' else 'the CPU port'} "
+                      f"at population_size={r['sample_P']} of {P}, scaled linearly in P; {r['cores']} torch threads of "
+                      f"{os.cpu_count()} cpus; {r['seconds_per_generation_sample']:.2f} s/sample-generation"}
+    if extras is not None:
+        line["extra"] = extras
+    emit(line)
+
+
+def kernel_rooflines(es, wl, args, world, rank, peaks):
+    """Per-kernel device time (CUDA events on the launching stream), geometry of this rank."""
+    from estorch_b200.backend import adam_desc
+    be, P, sigma, B, dims = es._be, wl["population_size"], wl["sigma"], wl["batch"], wl["dims"]
+    n, pairs, pl, slot = n_params(wl), P // 2, es._pairs_local, es._slots[0]
 
     def timed(fn, iters=5):
         for _ in range(2):
@@ -256,7 +407,6 @@ def run_ours(args, wl, rank, world, local_rank):
         torch.cuda.synchronize()
         return sorted(a.elapsed_time(b) for a, b in evs)[iters // 2]
 
-    from estorch_b200.backend import adam_desc
     R = es._returns if world == 1 else es._rm_buffers()[0]
     gt = es._grad_table()                       # the exact fp16 copy of the table when there is one
     tbytes = gt.element_size()
@@ -281,56 +431,42 @@ def run_ours(args, wl, rank, world, local_rank):
     bytes_grad = tbytes * n * pl + 28 * n + 8 * P
     bytes_eval = tbytes * n * pl + 4 * n + 4 * B * (dims[0] + dims[-1]) + 4 * P
     flops_eval = 2.0 * n * B * 2 * pl
-    k_grad = {"kernel": "rank_grad_adam" if world == 1 else "rank_grad", "bound": "hbm",
-              "achieved": bytes_grad / t_grad / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
-              "frac": bytes_grad / t_grad / 1e6 / peaks["hbm"], "ms": t_grad, "traffic": None,
-              "algorithmic_bytes": bytes_grad,
-              "note": "frac > 1 is L2 reuse: the rows of one generation overlap in the 1 GiB table and every CTA "
-                      "walks the pairs in offset-sorted order, so the table is fetched from HBM once (ncu: 1.08 GB "
-                      "DRAM read per launch) and the other 7/8 of the algorithmic bytes are L2 hits"}
-    k_eval = {"kernel": "eval_mlp_" + es._precision, "bound": "tensor", "achieved": flops_eval / t_eval / 1e9,
-              "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": flops_eval / t_eval / 1e9 / peaks["tensor"],
-              "ms": t_eval, "traffic": None, "algorithmic_bytes": bytes_eval, "flops": flops_eval,
-              "hbm_frac_of_noise_stream": bytes_eval / t_eval / 1e6 / peaks["hbm"]}
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
-    # `ncu --set full` capture of exactly these kernels / shapes on one GPU
-    # (profiles/ncu_traffic.json <- profiles/r01s2_ncu_full_summary.txt); null elsewhere
+    # `ncu --set full` capture of exactly these kernels / shapes on one GPU (profiles/ncu_traffic.json)
+    traffic = {}
     if args.workload == "north_star" and world == 1:
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            k_grad["traffic"] = tr.get(k_grad["kernel"])
-            k_eval["traffic"] = tr.get(k_eval["kernel"])
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except (OSError, ValueError):
-            pass
+            traffic = {}
+    kname_g = ("rank_grad_adam" if world == 1 else "rank_grad") + ("_h" if tbytes == 2 else "")
+    tr_g = traffic.get(kname_g)
+    k_grad = {"kernel": kname_g, "bound": "l2",
+              "achieved": bytes_grad / t_grad / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
+              "frac": bytes_grad / t_grad / 1e6 / peaks["hbm"],
+              "frac_algorithmic_vs_hbm": bytes_grad / t_grad / 1e6 / peaks["hbm"],
+              "frac_dram_vs_hbm": (tr_g / t_grad / 1e6 / peaks["hbm"]) if tr_g else None,
+              "ms": t_grad, "traffic": tr_g,
+              "traffic_source": "committed ncu capture (profiles/ncu_traffic.json)" if tr_g else None,
+              "algorithmic_bytes": bytes_grad,
+              "note": "algorithmic/HBM > 1 is L2 reuse: the rows of one generation overlap in the table and every CTA "
+                      "walks the pairs in offset-sorted order, so the table is fetched from HBM about once per launch "
+                      "and the rest of the algorithmic bytes are L2 hits; the binding resource is L2 bandwidth / "
+                      "bytes in flight, not HBM"}
+    kname_e = "eval_mlp_" + es._precision
+    k_eval = {"kernel": kname_e, "bound": "tensor", "achieved": flops_eval / t_eval / 1e9,
+              "peak": peaks["tensor_burst"], "peak_kind": "burst (the kernel is timed alone)", "unit": "TFLOP/s",
+              "frac": flops_eval / t_eval / 1e9 / peaks["tensor_burst"],
+              "frac_of_sustained_peak": flops_eval / t_eval / 1e9 / peaks["tensor"],
+              "ms": t_eval, "traffic": traffic.get(kname_e),
+              "traffic_source": "committed ncu capture (profiles/ncu_traffic.json)" if traffic.get(kname_e) else None,
+              "algorithmic_bytes": bytes_eval, "flops": flops_eval,
+              "hbm_frac_of_noise_stream": bytes_eval / t_eval / 1e6 / peaks["hbm"]}
     dominant = k_eval if t_eval >= t_grad else k_grad
-    roofline = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+    roofline = {k: dominant.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
     roofline["kernel"] = dominant["kernel"]
-    roofline["peak_source"] = peaks["source"]
-
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(wl, steps=1, warmup=0, budget_s=15.0)
-        cpu = {"value": r["value"], "unit": "generations/s", "cores": r["cores"], "kind": "port",
-               "sample": f"1 generation at population_size={r['sample_P']} of {P}, scaled linearly in P; "
-                         f"{r['cores']} torch threads of {os.cpu_count()} cpus; "
-                         f"{r['seconds_per_generation_sample']:.2f} s/sample-generation"}
-    line = {"metric": "generations/sec at pop=4096, 1M-param MLP", "value": args.steps / (ms / 1e3),
-            "unit": "generations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None,
-            "dtype": {"f16": "f32 (fp32-equivalent: evaluate GEMMs on tcgen05 with fp16 operands = 11-bit significand, "
-                             "TF32 class, each weight formed in fp32 from fp32 theta + the exactly-16-bit noise value and "
-                             "rounded once, f32 accumulate, f32 bias/loss; f32 ranks, reduction, Adam)",
-                      "bf16": "bf16 operands / f32 accumulate (evaluate GEMMs); f32 noise, ranks, reduction, Adam",
-                      "bf16s": "bf16 operands formed from bf16 shadows of theta/noise, f32 accumulate (evaluate "
-                               "GEMMs); f32 noise table, ranks, reduction, Adam"}.get(es._precision, "f32"),
-            "data": "synthetic", "config": workload_config(args, wl, world),
-            "e2e": {"value": args.steps / e2e_s, "unit": "generations/s",
-                    "h2d_bytes_per_step": int(obs.numel() * 4 + tgt.numel() * 4),
-                    "d2h_bytes_per_step": int(4 * P + 32)},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": [k_grad, k_eval],
-            "cpu_baseline": cpu}
-    emit(line)
+    roofline["peak_source"] = peaks["source"] + (", bf16 burst" if dominant is k_eval else "")
+    return {"roofline": roofline, "kernels": [k_grad, k_eval]}
 
 
 _JSON_FD = None
@@ -348,12 +484,13 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
     ap.add_argument("--table-log2", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--eval-precision", default="auto", choices=["auto", "fp32", "f16", "bf16", "bf16s"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -504,66 +504,70 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     setmaxnreg_inc<kRegsProd>();
     const int pwarp = warp - kProdWarp0;
     const int pgroup = pwarp / kProdGroupWarps;
-    const int ptid = (pwarp % kProdGroupWarps) * 32 + lane;   // thread index inside the group
     constexpr int kRS = kPT / 8;             // tile rows covered by one item step of the group
     constexpr int kIU = 128 / kRS;           // item steps per (full) stage
 #ifndef ESTK_F16_FB
 #define ESTK_F16_FB 2
 #endif
     constexpr int kFB = ESTK_F16_FB;         // rows formed per step (ld.shared batch)
-    const int r0 = ptid >> 3, c8 = ptid & 7;
-    // byte offsets inside a slot of the two 16-byte theta chunks this thread reads (row r0; rows
-    // r0 + u*kRS add u*kRS*128: kRS is a multiple of 8, the swizzle term does not change).  The
-    // lanes with c8 >= 4 read their pair in the opposite order: the eight lanes of a row then hit
-    // eight different 16-byte bank groups in each of the two ld.shared (no conflicts).
-    const int ch0 = 2 * (c8 & 3) + (c8 >> 2), ch1 = 2 * (c8 & 3) + 1 - (c8 >> 2);
-    const uint32_t roff0 = sw128_offset(r0, ch0), roff1 = sw128_offset(r0, ch1);
+    // Lane -> (row, chunk).  A warp covers 4 rows x 8 output chunks; a quarter-warp (the unit a 128-bit
+    // shared-memory access is served in) covers chunks 4h..4h+3 (h = which theta half they come from)
+    // of TWO rows whose indices differ by XOR 5 inside the 8-row swizzle group: the 128B swizzle then
+    // maps the quarter's eight 16-byte accesses to eight different bank groups, for the two theta
+    // loads (chunks 2c', 2c'+1 of half h) and for the fp16 store (chunk 4h+c') alike -- no conflicts,
+    // no per-lane reordering.  All eight writers of a row (and the readers of its half A) stay in one warp.
+    const int wg = pwarp % kProdGroupWarps, wq = lane >> 3, li = lane & 7;
+    const int hsel = wq & 1, cq = li & 3;
+    const int r0 = 8 * (wg >> 1) + ((2 * (wg & 1) + (wq >> 1)) ^ ((li >> 2) * 5)), c8 = 4 * hsel + cq;
+    static_assert(kRS == 8 || kRS == 16, "row mapping assumes 2 or 4 warps per producer group");
+    const uint32_t roff0 = sw128_offset(r0, 2 * cq), roff1 = sw128_offset(r0, 2 * cq + 1);
     const uint32_t woff = sw128_offset(r0, c8);               // the fp16 output chunk
     struct St { const uint16_t* ep; int k_rs; int rows; float sg; uint32_t kst; };
-    int cached_task = -1;
-    const uint16_t* cached_trow16 = nullptr;
-    float cached_ssig = 0.f;
-    int task = cluster_id, l = 0, n0 = 0, kb = 0;
-    uint32_t counter = pgroup;                                // global stage index of the position (task,l,n0,kb)
-    auto advance = [&]() -> bool {
-      if (++kb >= lay[l].K / kBlockK) {
-        kb = 0;
-        n0 += 256;
-        if (n0 >= lay[l].N) {
-          n0 = 0;
-          if (++l == L) { l = 0; task += n_clusters; }
+    // position of a stage in the flattened (task, layer, n-tile, k-block) sequence
+    struct Pos { int task, l, n0, kb, nkb; };
+    auto step_pos = [&](Pos& q, int by) -> bool {               // `by` stages further; false past the last task
+      q.kb += by;
+      while (q.kb >= q.nkb) {
+        q.kb -= q.nkb;
+        q.n0 += 256;
+        if (q.n0 >= lay[q.l].N) {
+          q.n0 = 0;
+          if (++q.l == L) { q.l = 0; q.task += n_clusters; }
+          if (q.task >= p.n_tasks) return false;
         }
+        q.nkb = lay[q.l].K / kBlockK;
       }
-      return task < p.n_tasks;
+      return true;
     };
     // (noise row, signed sigma) of a task: two dependent global loads -- fetched one task ahead
-    int pf_task = -1;
-    const uint16_t* pf_trow16 = nullptr;
-    float pf_ssig = 0.f;
+    int cached_task = -1, pf_task = -1;
+    const uint16_t *cached_trow16 = nullptr, *pf_trow16 = nullptr;
+    float cached_ssig = 0.f, pf_ssig = 0.f;
     auto fetch_task = [&](int t, const uint16_t*& trow16, float& ssig) {
       const TaskId tk = decode_task(p, t, centre);
       const int j = (!tk.centre && p.order) ? p.order[tk.slot] : tk.slot;
       trow16 = tk.centre ? nullptr : p.table16 + p.offsets[j];
       ssig = tk.centre ? 0.f : (tk.sgn ? -p.sigma : p.sigma);
     };
-    auto describe = [&](St& d) {             // descriptor of the stage at the current position
-      if (task != cached_task) {
-        cached_task = task;
-        if (task == pf_task) { cached_trow16 = pf_trow16; cached_ssig = pf_ssig; }
-        else fetch_task(task, cached_trow16, cached_ssig);
-        pf_task = task + n_clusters;         // consumed a whole task later: the loads never stall the pipeline
+    auto describe = [&](St& d, const Pos& q, uint32_t kst) {   // full descriptor of the stage at position q
+      if (q.task != cached_task) {
+        cached_task = q.task;
+        if (q.task == pf_task) { cached_trow16 = pf_trow16; cached_ssig = pf_ssig; }
+        else fetch_task(q.task, cached_trow16, cached_ssig);
+        pf_task = q.task + n_clusters;       // consumed a whole task later: the loads never stall the pipeline
         if (pf_task < p.n_tasks) fetch_task(pf_task, pf_trow16, pf_ssig);
       }
-      const int K = lay[l].K;
-      d.rows = min(256, lay[l].N - n0) / CG;                   // this CTA's share of the B tile
-      const int64_t rbase = lay[l].wbase + (int64_t)(n0 + (int)cta_rank * d.rows + r0) * K + kb * kBlockK + c8 * 8;
+      const int K = lay[q.l].K;
+      d.rows = min(256, lay[q.l].N - q.n0) / CG;               // this CTA's share of the B tile
+      const int64_t rbase = lay[q.l].wbase + (int64_t)(q.n0 + (int)cta_rank * d.rows + r0) * K + q.kb * kBlockK + c8 * 8;
       d.ep = cached_trow16 ? cached_trow16 + rbase : nullptr;
       d.k_rs = K * kRS;
       d.sg = cached_ssig;
-      d.kst = counter;
+      d.kst = kst;
     };
-    bool has_cur = task < p.n_tasks;
-    for (int sk = 0; sk < pgroup && has_cur; ++sk) has_cur = advance();
+    Pos pos = {cluster_id, 0, 0, 0, lay[0].K / kBlockK};
+    bool has_cur = pos.task < p.n_tasks;
+    if (has_cur && pgroup) has_cur = step_pos(pos, pgroup);
     uint4 E[kIU];
     auto load_eps = [&](const St& d, int u, uint4& e) {
       e = make_uint4(0u, 0u, 0u, 0u);
@@ -580,18 +584,26 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     const long long tp0 = PPROF_T();
     St cur = {}, nxt = {};
     if (has_cur) {
-      describe(cur);
+      describe(cur, pos, (uint32_t)pgroup);
 #pragma unroll
       for (int u = 0; u < kIU; ++u) load_eps(cur, u, E[u]);
     }
     while (has_cur) {
+      // this group's next stage: kProdGroups k-blocks further -- inside the same N tile only the noise
+      // pointer and the stage index move (the common case); otherwise the full descriptor
       bool has_nxt = true;
-      for (int sk = 0; sk < kProdGroups && has_nxt; ++sk) has_nxt = advance();
-      counter += kProdGroups;
-      if (has_nxt) describe(nxt);
+      if (pos.kb + kProdGroups < pos.nkb) {
+        pos.kb += kProdGroups;
+        nxt = cur;
+        nxt.kst = cur.kst + kProdGroups;
+        if (nxt.ep) nxt.ep = cur.ep + kBlockK * kProdGroups;
+      } else {
+        has_nxt = step_pos(pos, kProdGroups);
+        if (has_nxt) describe(nxt, pos, cur.kst + kProdGroups);
+      }
       const uint32_t sa = slot_a(cur.kst), sb = slot_b(cur.kst), par = par_a(cur.kst);
       const uint32_t base_a = smem_u32(sB + sa * kStageBytes), base_b = smem_u32(sB + sb * kStageBytes);
-      const uint32_t rd = (c8 < 4) ? base_a : base_b;           // this thread's theta chunks live in half A or B
+      const uint32_t rd = hsel ? base_b : base_a;               // this thread's theta chunks live in half A or B
       const long long tw0 = PPROF_T();
       mbar_wait(smem_u32(bar_land + sa), par);                  // both theta halves of the stage have landed
       PPROF_ADD(7, tw0);
@@ -611,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
         uint32_t w[kFB][4];
 #pragma unroll
         for (int q = 0; q < kFB; ++q) {
-          const float4 t0 = (c8 < 4) ? ta[q] : tb[q], t1 = (c8 < 4) ? tb[q] : ta[q];      // k ascending
+          const float4 t0 = ta[q], t1 = tb[q];
           const uint4 e = E[ub + q];
           const float2 e0 = unpack_f16(e.x), e1 = unpack_f16(e.y), e2 = unpack_f16(e.z), e3 = unpack_f16(e.w);
           w[q][0] = pack_f16(fmaf(cur.sg, e0.x, t0.x), fmaf(cur.sg, e0.y, t0.y));
