@@ -46,7 +46,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+// Triage instrumentation (role cycle counters, ESTK_TC_DEBUG switches) exists only in builds made with
+// -DESTK_TC_PROFILE (ESTK_VARIANT=prof); the product library has no debug globals and reads no environment.
+#ifdef ESTK_TC_PROFILE
 __device__ unsigned long long g_tc_prof[32];   // ESTK_TC_DEBUG bit 8: per-role cycle counters of cluster 0 / CTA 0
+#define TC_PROF_ATOMIC(i, v) atomicAdd(&g_tc_prof[i], (unsigned long long)(v))
+#define TC_PROF_ENABLED 1
+#else
+#define TC_PROF_ATOMIC(i, v) ((void)(v))
+#define TC_PROF_ENABLED 0
+#endif
 
 namespace {
 
@@ -115,7 +124,7 @@ __device__ __forceinline__ TaskId decode_task(const EvalTCParams& p, int task, b
 }
 #define PROF_ON (prof)
 #define PROF_T() (PROF_ON ? clock64() : 0ll)
-#define PROF_ADD(i, t0) do { if (PROF_ON) atomicAdd(&g_tc_prof[i], (unsigned long long)(clock64() - (t0))); } while (0)
+#define PROF_ADD(i, t0) do { if (PROF_ON) TC_PROF_ATOMIC(i, clock64() - (t0)); } while (0)
 
 // 448 threads at 128 registers: the register file is allocated per 4 warps, so a 14-warp
 // block is charged as 16 warps and 144 registers per thread do not launch (measured)
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
   }
   __syncthreads();
   const bool centre = (p.offsets == nullptr);
-  const bool prof = (p.dbg & 8) && blockIdx.x == 0 && lane == 0;
+  const bool prof = TC_PROF_ENABLED && (p.dbg & 8) && blockIdx.x == 0 && lane == 0;
 
   if (warp == 0) {
     // =================================================================== MMA issuer
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           }
         }
       }
-      if (eprof) atomicAdd(&g_tc_prof[11], (unsigned long long)(clock64() - to0));
+      if (eprof) TC_PROF_ATOMIC(11, clock64() - to0);
       float loss = 0.f;
       const uint32_t trow_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int l = 0; l < L; ++l) {
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
         for (int o = etid; o < N; o += 32 * kNumEpiWarps)
           bias[o] = fmaf(ssig, ld_noise1(trow + lay[l].bbase + o), __ldg(p.theta + lay[l].bbase + o));
         named_bar_sync(1, 32 * kNumEpiWarps);   // publishes bias[] among the epilogue warps
-        if (eprof) atomicAdd(&g_tc_prof[12], (unsigned long long)(clock64() - tb0));
+        if (eprof) TC_PROF_ATOMIC(12, clock64() - tb0);
         const bool last = (l == L - 1);
         const bool two = N > 256;               // two N tiles: columns [0,256) and [256,N)
         // bias + ReLU + round to bf16: 32 accumulator columns -> 16 packed words
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           mbar_wait(smem_u32(bar_acc0), acc0_phase);
           acc0_phase ^= 1;
           tc_fence_after();
-          if (eprof) atomicAdd(&g_tc_prof[13], (unsigned long long)(clock64() - ta0));
+          if (eprof) TC_PROF_ATOMIC(13, clock64() - ta0);
           const long long tx0 = eprof ? clock64() : 0ll;
           for (int c0 = 0; c0 < 256; c0 += 32) {
             uint32_t va[32];
@@ -416,14 +425,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             }
           }
           if (!last) tmem_st_wait();
-          if (eprof) atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - tx0));
+          if (eprof) TC_PROF_ATOMIC(15, clock64() - tx0);
         }
         // ---- wait for the whole layer: every MMA that reads the activations has completed
         const long long ta1 = eprof ? clock64() : 0ll;
         mbar_wait(smem_u32(bar_acc), acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        if (eprof) atomicAdd(&g_tc_prof[13], (unsigned long long)(clock64() - ta1));
+        if (eprof) TC_PROF_ATOMIC(13, clock64() - ta1);
         const long long tx1 = eprof ? clock64() : 0ll;
         if (!last && two) {
           // parked half -> activation k-blocks 0..3, first hand-over
@@ -448,7 +457,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
           }
         }
         if (!last) hand_over();                  // second half (or the only one when N <= 256)
-        if (eprof) atomicAdd(&g_tc_prof[14], (unsigned long long)(clock64() - tx1));
+        if (eprof) TC_PROF_ATOMIC(14, clock64() - tx1);
       }
       // ---- squared-error partial of this CTA; the last arriver combines them in fixed order
       loss = warp_sum_f(loss);
@@ -476,7 +485,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       }
       named_bar_sync(2, 32 * kNumEpiWarps);   // s_loss reusable
     }
-    if (eprof) atomicAdd(&g_tc_prof[10], (unsigned long long)(clock64() - te0));
+    if (eprof) TC_PROF_ATOMIC(10, clock64() - te0);
   } else if (warp >= 2 + kNumEpiWarps) {
     // =================================================================== weight producers
     // The producer warps form kProdGroups groups; group g builds stages g, g+G, g+2G, ... of
@@ -536,7 +545,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
       const uint32_t stage = counter % kStages, ring_phase = (counter / kStages) & 1u;
       const long long ts0 = pprof ? clock64() : 0ll;
       setup(task, l, n0, kb, cur);
-      if (pprof) atomicAdd(&g_tc_prof[5], (unsigned long long)(clock64() - ts0));
+      if (pprof) TC_PROF_ATOMIC(5, clock64() - ts0);
       const uint32_t sbase = smem_u32(sB + stage * kStageB);
       bool waited = false;
       if constexpr (src16) {
@@ -555,7 +564,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             e16[u] = ld_noise4u(reinterpret_cast<const uint4*>(eptr + (size_t)(u * 8) * cur.K));
         const long long tw0 = pprof ? clock64() : 0ll;
         mbar_wait(smem_u32(bar_tma + stage), ring_phase);          // theta tile landed (so the slot was free)
-        if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
+        if (pprof) TC_PROF_ATOMIC(7, clock64() - tw0);
         const long long tc0 = pprof ? clock64() : 0ll;
         // W = theta16 + (s*sigma)_bf16 * eps16, one packed fma per two elements, in place
         // (exact product-sum, one rounding to bf16; sigma itself is rounded to bf16)
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             st_shared_v4(taddr + u * 1024, w[0], w[1], w[2], w[3]);
           }
         }
-        if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
+        if (pprof) TC_PROF_ATOMIC(8, clock64() - tc0);
       } else if constexpr (F16) {
         // fp32 theta + the exact fp16 copy of the noise row, both through registers:
         // W = rn_f16(theta + s*sigma*eps), the sum formed in fp32 (one rounding per weight)
@@ -595,7 +604,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             const long long tw0 = pprof ? clock64() : 0ll;
             mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
             waited = true;
-            if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
+            if (pprof) TC_PROF_ATOMIC(7, clock64() - tw0);
           }
           const long long tc0 = pprof ? clock64() : 0ll;
 #pragma unroll
@@ -612,7 +621,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
               st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
             }
           }
-          if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
+          if (pprof) TC_PROF_ATOMIC(8, clock64() - tc0);
         }
       } else {
       for (int it0 = 0; it0 < cur.n_items; it0 += 4 * kPT) {
@@ -633,7 +642,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
             const long long tw0 = pprof ? clock64() : 0ll;
             mbar_wait(smem_u32(bar_empty + stage), ring_phase ^ 1);
             waited = true;
-            if (pprof) atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - tw0));
+            if (pprof) TC_PROF_ATOMIC(7, clock64() - tw0);
           }
           const long long tc0 = pprof ? clock64() : 0ll;
   #pragma unroll
@@ -648,19 +657,19 @@ __global__ void __launch_bounds__(kThreadsTC, 1) eval_mlp_tc_kernel(const EvalTC
               st_shared_v4(sbase + sw128_offset(it >> 3, it & 7), w0, w1, w2, w3);
             }
           }
-          if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(clock64() - tc0));
+          if (pprof) TC_PROF_ATOMIC(8, clock64() - tc0);
         }
       }
       const long long tf0 = pprof ? clock64() : 0ll;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_full + stage), 0);
-      if (pprof) atomicAdd(&g_tc_prof[9], (unsigned long long)(clock64() - tf0));
+      if (pprof) TC_PROF_ATOMIC(9, clock64() - tf0);
       for (int sk = 0; sk < kProdGroups && has_cur; ++sk) has_cur = advance(task, l, n0, kb);
       counter += kProdGroups;
-      if (pprof) atomicAdd(&g_tc_prof[6], 1ull);
+      if (pprof) TC_PROF_ATOMIC(6, 1ull);
     }
-    if (pprof) atomicAdd(&g_tc_prof[4], (unsigned long long)(clock64() - tp0));
+    if (pprof) TC_PROF_ATOMIC(4, clock64() - tp0);
   }
 
   // ---- teardown
@@ -777,12 +786,18 @@ int run_tc(estk_ctx* ctx, EvalTCParams& p, cudaStream_t stream, const char* who)
   p.n_centre = p.centre_out ? p.chunks : 0;
   ESTK_CHECK_ARG(!p.centre_out || p.pairs * 2 < ESTK_MAX_POPULATION, "%s: population too large to fold the centre task", who);
   p.n_tasks = p.n_centre + p.pairs * p.n_signs * p.chunks;
+#ifdef ESTK_TC_PROFILE
   { const char* e = getenv("ESTK_TC_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+#endif
   p.partial = ctx->eval_partial;
   p.counters = ctx->counters;
   // B ring depth: bf16s runs 4 producer groups and wants the 5 stages that fit beside the
   // 128 KB of activations (ESTK_TC_RING=4|5 overrides; perf triage only)
+#ifdef ESTK_TC_PROFILE
   static const int ring_env = [] { const char* e = getenv("ESTK_TC_RING"); return e ? atoi(e) : 0; }();
+#else
+  constexpr int ring_env = 0;
+#endif
   static thread_local TcMaps maps;
   if (p.mode == kModeF16)
     return ring_env == 4 ? launch_tc<2, kModeF16, 4>(ctx, p, &maps, stream) : launch_tc<2, kModeF16, 5>(ctx, p, &maps, stream);
@@ -899,8 +914,12 @@ int estk_f16v2_eval(estk_ctx* ctx, const estk_mlp_desc* desc, const float* theta
                     float* bc_plus, float* bc_minus, int32_t bc_obs, int32_t bc_dim, float* centre_return_out,
                     int n_signs, cudaStream_t stream, const char* who);
 static bool f16_use_v1() {
+#ifdef ESTK_TC_PROFILE
   static const bool v1 = [] { const char* e = getenv("ESTK_F16_V1"); return e && atoi(e) != 0; }();
   return v1;
+#else
+  return false;
+#endif
 }
 __global__ void __launch_bounds__(256) shadow_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4,
                                                          unsigned long long* __restrict__ inexact) {
@@ -985,7 +1004,8 @@ extern "C" int estk_eval_mlp_bf16_supported(const estk_mlp_desc* desc, int32_t B
   return desc ? tc_supported(*desc, B, 2, &why) : 0;
 }
 
-// perf triage only (not part of estk.h): read and clear the cycle counters written when ESTK_TC_DEBUG has bit 8
+#ifdef ESTK_TC_PROFILE
+// triage builds only (not part of estk.h): read and clear the cycle counters written when ESTK_TC_DEBUG has bit 8
 extern "C" __attribute__((visibility("default"))) int estk_debug_tc_profile(unsigned long long* host_out, int n) {
   if (n > 32) n = 32;
   cudaDeviceSynchronize();
@@ -993,3 +1013,4 @@ extern "C" __attribute__((visibility("default"))) int estk_debug_tc_profile(unsi
   unsigned long long zeros[32] = {};
   return cudaMemcpyToSymbol(g_tc_prof, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -1;
 }
+#endif

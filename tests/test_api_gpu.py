@@ -253,3 +253,91 @@ def test_deferred_post_update_rollout_is_equivalent():
     assert [s for s, _, _ in b["seen"]] == [2, 5] and len(a["seen"]) == 7
     for step, ep, br in b["seen"]:                     # the logged generations report the same values
         assert (step, ep, br) == a["seen"][step]
+
+
+# ------------------------------------------------------------------ checkpoint / resume and the launcher, on the device
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_checkpoint_resume_is_bit_identical_on_device(tmp_path, precision):
+    """save_checkpoint() after 2 generations, 2 more; a fresh instance that loads the checkpoint and
+    runs 2 generations ends with bit-identical theta / Adam moments / best snapshot (the noise table is
+    regenerated from the seed, the generation counter and the Adam step live in estk_state)."""
+    dims = [128, 512, 288] if precision == "auto" else [4, 64, 64, 2]
+    g = torch.Generator().manual_seed(9)
+    obs, tgt = torch.randn(256, dims[0], generator=g), torch.randn(256, dims[-1], generator=g)
+
+    def make():
+        torch.manual_seed(3)
+        es = E.ES(MLP, E.DeviceAgent, torch.optim.Adam, population_size=64, sigma=0.05, policy_kwargs={"dims": dims},
+                  agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 20,
+                  eval_precision=precision, log_interval=2)
+        es.log = lambda: None
+        return es
+    a = make()
+    a.train(n_steps=2)
+    path = str(tmp_path / "ck.pt")
+    a.save_checkpoint(path)
+    a.train(n_steps=3)
+    b = make()
+    b.load_checkpoint(path)
+    assert b._generation == 2
+    b.train(n_steps=3)
+    sa, sb = a._slots[0], b._slots[0]
+    for x, y in ((sa.theta, sb.theta), (sa.m, sb.m), (sa.v, sb.v), (sa.best_theta, sb.best_theta)):
+        assert torch.equal(x, y)
+    assert a.best_reward == b.best_reward and a.episode_reward == b.episode_reward and a._generation == b._generation == 5
+    np.testing.assert_array_equal(a.population_returns, b.population_returns)
+
+
+def test_graph_replay_equals_eager(monkeypatch):
+    """A generation replayed from a CUDA graph (the default after the first sighting of a configuration)
+    leaves exactly the state the eager launches leave."""
+    dims = [128, 512, 288]
+    g = torch.Generator().manual_seed(2)
+    obs, tgt = torch.randn(256, 128, generator=g), torch.randn(256, 288, generator=g)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("ESTORCH_B200_GRAPH", mode)
+        torch.manual_seed(4)
+        es = E.ES(MLP, E.DeviceAgent, torch.optim.Adam, population_size=128, sigma=0.02, policy_kwargs={"dims": dims},
+                  agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22,
+                  log_interval=4)
+        es.log = lambda: None
+        es.train(n_steps=9)
+        out[mode] = (es._slots[0].theta.clone(), es._slots[0].best_theta.clone(), es.episode_reward, es.best_reward,
+                     es.population_returns.copy(), len(es.__dict__.get("_graphs", {})))
+    a, b = out["1"], out["0"]
+    assert a[5] >= 1 and b[5] == 0                       # graphs were actually used / not used
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
+    np.testing.assert_array_equal(a[4], b[4])
+
+
+def test_train_n_proc_2_reexecs_under_torchrun(tmp_path):
+    """train(n_proc=2) in a plain `python script.py` re-executes the script under torch.distributed.run with
+    one process per GPU, like the reference's _fork under mpirun (estorch.py:41-56, :305); both ranks end with
+    the same parameters and rank 0 alone logs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, os, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "user_script.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, numpy as np, torch
+        sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+        import estorch_b200 as E
+        from test_api_cpu import MLP
+        g = torch.Generator().manual_seed(1)
+        obs, tgt = torch.randn(256, 128, generator=g), torch.randn(256, 288, generator=g)
+        class Q(E.ES):
+            def log(self):
+                open(os.path.join({str(tmp_path)!r}, f"log_rank{{self.rank}}.txt"), "a").write(f"{{self.step}}\\n")
+        es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=256, sigma=0.02, policy_kwargs={{"dims": [128, 512, 288]}},
+               agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={{"lr": 0.01}}, noise_table_size=1 << 22)
+        es.train(n_steps=3, n_proc=2)
+        torch.cuda.synchronize()
+        np.save(os.path.join({str(tmp_path)!r}, f"theta_rank{{es.rank}}.npy"), es._slots[0].theta.cpu().numpy())
+    """))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    t0, t1 = np.load(tmp_path / "theta_rank0.npy"), np.load(tmp_path / "theta_rank1.npy")
+    np.testing.assert_array_equal(t0, t1)
+    assert (tmp_path / "log_rank0.txt").read_text().split() == ["0", "1", "2"] and not (tmp_path / "log_rank1.txt").exists()
