@@ -205,7 +205,7 @@ class CudaBackend:
         else:
             raise ValueError(f"unknown precision {precision!r}")
         _capi.check(rc, "estk_eval_mlp[" + precision + "]")
-        self.launches += 1
+        self.launches += 2 if precision == "f16" else 1      # f16: observation image + evaluate
 
     def eval_mlp_center(self, dims, theta, obs, target, ret_out, bc_out=None, bc_obs=0, bc_dim=0,
                         precision="fp32", theta16=None):
@@ -224,7 +224,7 @@ class CudaBackend:
         else:
             rc = self.lib.estk_eval_mlp_center(self._ctx, C.byref(d), th, *tail)
         _capi.check(rc, "estk_eval_mlp_center[" + precision + "]")
-        self.launches += 1
+        self.launches += 2 if precision == "f16" else 1
 
     def conv_scratch_bytes(self, ref_batch, B) -> int:
         return int(self.lib.estk_eval_conv_vbn_scratch_bytes(self._ctx, int(ref_batch), int(B)))

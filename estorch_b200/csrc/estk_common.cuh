@@ -44,8 +44,11 @@ struct estk_ctx {
   float* eval_partial;     // [ESTK_MAX_POPULATION * kEvalMaxChunks] loss partials
   unsigned int* counters;  // [ESTK_MAX_POPULATION + 8] self-resetting arrival counters (+ kernel tickets)
   double* scalars;         // [8] small fp64 scratch (||archive||_F, ...)
+  void* obs_image;         // [kObsImageBytes] fp16 hi/lo image of the observation batch, laid out as the
+                           // evaluate kernel's layer-0 shared-memory operand (estk_eval_mlp_f16.cu)
 };
 static const int kEvalMaxChunks = 64;
+static const size_t kObsImageBytes = (size_t)kEvalMaxChunks * 8 * 16384;   // 128-row blocks x 8 k-blocks x 16 KB
 
 // ---------------------------------------------------------------- hashing
 // splitmix64 finaliser; must stay in lock-step with oracle/es_oracle.py:mix64

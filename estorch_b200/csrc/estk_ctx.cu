@@ -44,6 +44,7 @@ extern "C" int estk_ctx_create(int device, estk_ctx** out) {
     e = cudaMalloc(&c->eval_partial, sizeof(float) * (size_t)ESTK_MAX_POPULATION * kEvalMaxChunks);
   if (e == cudaSuccess) e = cudaMalloc(&c->counters, sizeof(unsigned int) * (ESTK_MAX_POPULATION + 8));
   if (e == cudaSuccess) e = cudaMalloc(&c->scalars, sizeof(double) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&c->obs_image, kObsImageBytes);
   if (e == cudaSuccess) e = cudaMemset(c->counters, 0, sizeof(unsigned int) * (ESTK_MAX_POPULATION + 8));
   if (e != cudaSuccess) {
     estk_set_error("estk_ctx_create: workspace allocation failed: %s", cudaGetErrorString(e));
@@ -61,6 +62,7 @@ extern "C" int estk_ctx_destroy(estk_ctx* c) {
   cudaFree(c->eval_partial);
   cudaFree(c->counters);
   cudaFree(c->scalars);
+  cudaFree(c->obs_image);
   delete c;
   return ESTK_OK;
 }

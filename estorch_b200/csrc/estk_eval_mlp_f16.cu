@@ -8,7 +8,9 @@
 // noise value (streamed from the EXACT 16-bit copy of the table) and rounded ONCE to fp16 (11-bit
 // significand, the TF32 class); hidden activations are rounded to fp16 when they are written back
 // (bias + ReLU in fp32 first); the observations enter layer 0 as x_hi + x_lo (two fp16 operands on
-// the same weight tile); accumulation, bias, squared error in fp32.
+// the same weight tile; their shared-memory image is built once per launch by stage_obs_f16_kernel
+// and dropped into the activation buffer by one bulk copy per task, issued while the previous
+// task's loss is still being reduced); accumulation, bias, squared error in fp32.
 //
 // Work unit ("task") = (antithetic pair j, sign s, chunk of 256 observations) on a cluster of two
 // CTAs, tcgen05.mma.cta_group::2, UMMA M = 256 (128 observation rows per CTA).  Per layer
@@ -98,6 +100,8 @@ struct EvalF16Params {
   int pairs;
   float sigma;
   const float* obs;
+  const uint8_t* obs_image;  // fp16 hi/lo image of obs, one [2*K0/64 k-blocks x 16 KB] block per 128 observations,
+                             // already in the layer-0 operand layout (stage_obs_f16_kernel)
   const float* target;
   int B, chunks;             // chunks of 128*CG observations
   float* ret_plus;
@@ -145,7 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
   uint64_t* bar_acc0 = bars + 4 * kSlots;      // first N tile of a two-tile layer accumulated   (local)
   uint64_t* bar_acc = bars + 4 * kSlots + 1;   // layer accumulated                              (local)
   uint64_t* bar_h = bars + 4 * kSlots + 2;     // [2] next layer's k-blocks 0..3 / 4..7 in place (leader's are used)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4 * kSlots + 4);
+  uint64_t* bar_obs = bars + 4 * kSlots + 4;   // the next task's observation image has landed   (local)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4 * kSlots + 5);
   float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kEpiWarps]
   __shared__ Layer lay[ESTK_MAX_LAYERS];
 
@@ -165,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     mbar_init(smem_u32(bar_acc), 1);
     mbar_init(smem_u32(bar_h + 0), CG * kEpiWarps);
     mbar_init(smem_u32(bar_h + 1), CG * kEpiWarps);
+    mbar_init(smem_u32(bar_obs), 1);
     fence_barrier_init();
   }
   if (threadIdx.x == 32) {          // per-layer geometry, in shared memory
@@ -301,6 +307,18 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
       __syncwarp();
       if (lane == 0) mbar_arrive_on<CG>(smem_u32(bar_h + idx), 0);
     };
+    uint32_t obs_phase = 0;
+    const uint32_t obs_bytes = (uint32_t)(2 * lay[0].K / kBlockK) * kKBlockBytes;   // hi + lo k-blocks
+    auto issue_obs = [&](int t) {               // one thread of the CTA: bulk copy of task t's observation block
+      if (ew == 0 && lane == 0) {
+        const TaskId tq = decode_task(p, t, centre);
+        const uint8_t* src = p.obs_image + (size_t)(tq.chunk * CG + (int)cta_rank) * obs_bytes;
+        fence_proxy_async();                    // earlier generic-proxy writes to these bytes (activations) are ordered first
+        mbar_arrive_expect_tx(smem_u32(bar_obs), obs_bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sH)), "l"(src), "r"(obs_bytes), "r"(smem_u32(bar_obs)) : "memory");
+      }
+    };
     for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
       const long long to0 = EPROF_T();
       const TaskId tk = decode_task(p, task, centre);
@@ -309,38 +327,13 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
       const float* trow = tk.centre ? p.theta : p.table + p.offsets[j];
       const float ssig = tk.centre ? 0.f : (sgn ? -p.sigma : p.sigma);
       const int b = (chunk * CG + (int)cta_rank) * 128 + row;      // global observation index
-      // ---- stage this CTA's observations as the layer-0 A operand: x = x_hi + x_lo (fp16 each);
-      //      the two warps of a lane quarter split the 16-byte chunks of a row
-      {
-        const int K0 = lay[0].K;
-        const float* orow = p.obs + (size_t)b * K0;
-        const int cper = K0 / 16;                                  // 8-element chunks per warp (K0/8 in total)
-        for (int cc = 0; cc < cper; cc += 4) {
-          float4 x[4][2];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (cc + u < cper) {
-              const int c = half * cper + cc + u;
-              x[u][0] = __ldg(reinterpret_cast<const float4*>(orow + c * 8));
-              x[u][1] = __ldg(reinterpret_cast<const float4*>(orow + c * 8 + 4));
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (cc + u < cper) {
-              const int c = half * cper + cc + u;
-              const uint32_t off = sw128_offset(row, c & 7);
-              const uint32_t h0 = pack_f16(x[u][0].x, x[u][0].y), h1 = pack_f16(x[u][0].z, x[u][0].w);
-              const uint32_t h2 = pack_f16(x[u][1].x, x[u][1].y), h3 = pack_f16(x[u][1].z, x[u][1].w);
-              st_shared_v4(smem_u32(sH + (c >> 3) * kKBlockBytes) + off, h0, h1, h2, h3);
-              const float2 f0 = unpack_f16(h0), f1 = unpack_f16(h1), f2 = unpack_f16(h2), f3 = unpack_f16(h3);
-              st_shared_v4(smem_u32(sH + ((c >> 3) + K0 / kBlockK) * kKBlockBytes) + off,
-                           pack_f16(x[u][0].x - f0.x, x[u][0].y - f0.y), pack_f16(x[u][0].z - f1.x, x[u][0].w - f1.y),
-                           pack_f16(x[u][1].x - f2.x, x[u][1].y - f2.y), pack_f16(x[u][1].z - f3.x, x[u][1].w - f3.y));
-            }
-          }
-        }
-      }
+      // ---- this CTA's observations as the layer-0 A operand, x = x_hi + x_lo (fp16 each): the image was
+      //      built once per launch (stage_obs_f16_kernel) in exactly the shared-memory layout and is
+      //      dropped into the activation buffer by ONE bulk copy, issued as soon as the previous task's
+      //      last MMAs were done (see below) -- normally it has landed long before this wait
+      if (task == cluster_id) issue_obs(task);
+      mbar_wait(smem_u32(bar_obs), obs_phase);
+      obs_phase ^= 1;
       EPROF_ADD(11, to0);
       // the staged observations are this task's layer-0 input (the previous task's TMEM reads are
       // long done): release the MMA warp before anything else
@@ -434,6 +427,9 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
         acc_phase ^= 1;
         tc_fence_after();
         EPROF_ADD(13, ta1);
+        // nothing reads the activation buffer any more in this task: the next task's observations can land
+        // while the loss is computed from TMEM
+        if (last && task + n_clusters < p.n_tasks) issue_obs(task + n_clusters);
         const long long tx1 = EPROF_T();
         if (!last && two) {
           // parked half -> activation k-blocks (2*half, 2*half+1); hand-over 0 when both halves are in
@@ -660,9 +656,31 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
   if (warp == 1) tmem_dealloc<CG>(tmem_base, 512);
 }
 
+// fp16 hi/lo image of the observation batch in the layer-0 operand layout: per block of 128 observations
+// (one CTA's rows of one chunk) 2*K0/64 k-blocks of 16 KB -- x_hi k-blocks first, then x_lo = rn_f16(x - x_hi);
+// inside a k-block row r, 16-byte chunk c sits at sw128_offset(r, c).  One thread per (observation, 8 elements).
+__global__ void __launch_bounds__(256) stage_obs_f16_kernel(const float* __restrict__ obs, uint8_t* __restrict__ image,
+                                                            int B, int K0) {
+  const int per_row = K0 / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * per_row) return;
+  const int b = idx / per_row, c = idx % per_row;
+  const float4 x0 = __ldg(reinterpret_cast<const float4*>(obs + (size_t)b * K0 + c * 8));
+  const float4 x1 = __ldg(reinterpret_cast<const float4*>(obs + (size_t)b * K0 + c * 8 + 4));
+  const uint32_t h0 = pack_f16(x0.x, x0.y), h1 = pack_f16(x0.z, x0.w), h2 = pack_f16(x1.x, x1.y), h3 = pack_f16(x1.z, x1.w);
+  const float2 f0 = unpack_f16(h0), f1 = unpack_f16(h1), f2 = unpack_f16(h2), f3 = unpack_f16(h3);
+  const int nkb = K0 / kBlockK;
+  uint8_t* blk = image + (size_t)(b / 128) * (size_t)(2 * nkb) * kKBlockBytes;
+  const uint32_t off = sw128_offset(b % 128, c & 7);
+  *reinterpret_cast<uint4*>(blk + (size_t)(c >> 3) * kKBlockBytes + off) = make_uint4(h0, h1, h2, h3);
+  *reinterpret_cast<uint4*>(blk + (size_t)((c >> 3) + nkb) * kKBlockBytes + off) =
+      make_uint4(pack_f16(x0.x - f0.x, x0.y - f0.y), pack_f16(x0.z - f1.x, x0.w - f1.y),
+                 pack_f16(x1.x - f2.x, x1.y - f2.y), pack_f16(x1.z - f3.x, x1.w - f3.y));
+}
+
 size_t f16_smem_bytes() {
   return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)kSlots * kStageBytes + 2 * kMaxW * sizeof(float) +
-         (4 * kSlots + 4) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + kEpiWarps * sizeof(float) + 64;
+         (4 * kSlots + 5) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + kEpiWarps * sizeof(float) + 64;
 }
 
 // ---- TMA descriptors of the fp32 theta (host side)
@@ -749,6 +767,14 @@ int run_f16(estk_ctx* ctx, EvalF16Params& p, cudaStream_t stream, const char* wh
 #endif
   static thread_local ThetaMaps maps;
   { const int rc = build_theta_maps(p.desc, p.theta, &maps); if (rc != ESTK_OK) return rc; }
+  {   // the observation image of this launch (a few hundred KB: negligible next to the evaluate)
+    const int K0 = p.desc.dims[0];
+    ESTK_CHECK_ARG((size_t)(p.B / 128) * (size_t)(2 * K0 / kBlockK) * kKBlockBytes <= kObsImageBytes, "%s: batch too large", who);
+    const int items = p.B * (K0 / 8);
+    stage_obs_f16_kernel<<<(items + 255) / 256, 256, 0, stream>>>(p.obs, reinterpret_cast<uint8_t*>(ctx->obs_image), p.B, K0);
+    ESTK_CUDA(cudaGetLastError());
+    p.obs_image = reinterpret_cast<const uint8_t*>(ctx->obs_image);
+  }
   const size_t smem = f16_smem_bytes();
   ESTK_CUDA(cudaFuncSetAttribute(eval_mlp_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int clusters = ctx->sm_count / CG;

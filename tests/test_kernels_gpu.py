@@ -252,6 +252,54 @@ def test_rank_ties_stable_by_index(be):
     np.testing.assert_array_equal(out["ranks"], orc.compute_ranks(ret))
 
 
+@pytest.mark.parametrize("n,P,W", [(1001760, 512, 4), (6020, 256, 2), (4610, 64, 1)])
+def test_rank_grad_fp16_table_and_rank_major_layout(be, n, P, W):
+    """estk_rank_grad[_adam]_h stream the EXACT fp16 copy of the table: same ranks, and the same gradient /
+    theta as the fp32-table entry points (bit-identical when both take the column-split path, i.e. large n;
+    a different pair split for small n only changes the fp32 summation order).  With world = W the returns
+    arrive rank-major [W][2][pairs/W] (what the in-place all-gather produces): ranks_out stays in member order."""
+    from estorch_b200.backend import new_state, adam_desc
+    rng = np.random.RandomState(5)
+    table_len = (n + 31) // 32 * 32 + (1 << 16)
+    table = orc.round_f16(rng.standard_normal(table_len).astype(np.float32))
+    offs = orc.noise_offsets(3, 1, 0, P // 2, table_len, n)
+    order = np.argsort(offs, kind="stable").astype(np.int32)
+    ret = rng.standard_normal(P).astype(np.float32)
+    ret[5] = ret[P // 2 + 7]                                   # a tie: broken by member index in every layout
+    theta = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    tb = dev(be, table)
+    tb16 = be.alloc(table_len, dtype=torch.float16)
+    assert be.shadow_f16(tb, tb16) == 0
+    res = {}
+    for name, t in (("fp32", tb), ("fp16", tb16)):
+        th, mm, vv = dev(be, theta), be.zeros(n), be.zeros(n)
+        ranks, g = be.zeros(P, dtype=torch.int32), be.zeros(n)
+        be.rank_grad_adam(dev(be, ret), None, 1.0, 0.0, P, t, dev(be, offs), dev(be, order), th, mm, vv,
+                          new_state(be.device), adam_desc(lr=0.01), ranks, None, g)
+        res[name] = (ranks.cpu().numpy(), g.cpu().numpy(), th.cpu().numpy())
+    np.testing.assert_array_equal(res["fp16"][0], res["fp32"][0])
+    np.testing.assert_array_equal(res["fp16"][0], orc.compute_ranks(ret))
+    if n > 500000:
+        np.testing.assert_array_equal(res["fp16"][1], res["fp32"][1])
+        np.testing.assert_array_equal(res["fp16"][2], res["fp32"][2])
+    else:
+        assert rel_err(res["fp16"][1], res["fp32"][1]) < 2e-6
+    # sharded + rank-major: sum of the shards' raw partial sums / P == the fused gradient
+    pairs, pl = P // 2, P // 2 // W
+    rm = np.empty((W, 2, pl), np.float32)
+    for r in range(W):
+        rm[r, 0], rm[r, 1] = ret[r * pl:(r + 1) * pl], ret[pairs + r * pl: pairs + (r + 1) * pl]
+    total = be.zeros(n)
+    for r in range(W):
+        part, ranks = be.zeros(n), be.zeros(P, dtype=torch.int32)
+        so = offs[r * pl:(r + 1) * pl]
+        be.rank_grad(dev(be, rm.reshape(-1)), None, 1.0, 0.0, P, tb16, dev(be, so),
+                     dev(be, np.argsort(so, kind="stable").astype(np.int32)), r * pl, pl, n, part, ranks, None, world=W)
+        np.testing.assert_array_equal(ranks.cpu().numpy(), res["fp32"][0])
+        total += part
+    assert rel_err((total / P).cpu().numpy(), res["fp32"][1]) < 2e-6
+
+
 def test_sharded_rank_grad_equals_fused(be):
     """Multi-GPU form on one GPU: sum of per-shard raw partials -> clamp_adam
     equals the fused kernel (this is what the NCCL all-reduce computes)."""

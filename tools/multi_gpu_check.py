@@ -1,5 +1,6 @@
-"""Launched with torchrun on W GPUs: fused ES and fused NSRA-ES stay bit-identical across
-ranks on real NCCL, and match a single-GPU run of the same problem on rank 0's device."""
+"""Launched with torchrun on W GPUs (real NCCL): fused ES and fused NSRA-ES stay bit-identical across ranks
+although every rank constructs DIFFERENT initial policies (rank 0's state is broadcast before the loop), and a
+generation replayed from a CUDA graph -- collectives included -- leaves exactly what the eager launches leave."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,27 +11,39 @@ from test_api_cpu import MLP
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl")
-g = torch.Generator().manual_seed(3)
-for name, cls, dims, kw, akw in (("ES", E.ES, [128, 512, 288], {}, {}),
-                                 ("NSRA_ES", E.NSRA_ES, [24, 64, 64, 4], {"weight_t": 2}, {"bc_obs": 64, "bc_dim": 256})):
-    obs, tgt = torch.randn(256, dims[0], generator=g), torch.randn(256, dims[-1], generator=g)
-    torch.manual_seed(5); np.random.seed(11)
+results = {}
+CASES = (("ES", E.ES, [128, 512, 288], {}, {}),
+         ("NSRA_ES", E.NSRA_ES, [24, 64, 64, 4], {"weight_t": 2}, {"bc_obs": 64, "bc_dim": 256}))
+for graph in ("1", "0"):
+    os.environ["ESTORCH_B200_GRAPH"] = graph
+    for name, cls, dims, kw, akw in CASES:
+        g = torch.Generator().manual_seed(3)
+        obs, tgt = torch.randn(256, dims[0], generator=g), torch.randn(256, dims[-1], generator=g)
+        torch.manual_seed(5 + rank)       # a different initial policy on every rank ...
+        np.random.seed(11)                # ... (the meta-policy draw of NS runs on rank 0 only and is broadcast)
 
-    class Q(cls):
-        def log(self):
-            pass
-    es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=256, sigma=0.02, policy_kwargs={"dims": dims},
-           agent_kwargs=dict(obs=obs, target=tgt, **akw), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22,
-           log_interval=int(os.environ.get("LOG_INTERVAL", "1")), **kw)   # > 1: the post-update rollout is folded
-    assert es._fused and es.n_workers == world
-    es.train(n_steps=3)
-    theta = torch.stack([s.theta for s in es._slots])
-    ret = torch.from_numpy(es.population_returns).to(theta.device)
-    for t in (theta, ret):
-        ref = t.clone(); dist.broadcast(ref, src=0)
-        assert torch.equal(ref, t), f"{name}: rank {rank} diverged from rank 0"
-    assert torch.isfinite(theta).all() and torch.isfinite(ret).all()
-    if rank == 0:
-        print(f"{name}: {world} ranks bit-identical after 3 generations; precision={es._precision}; "
-              f"episode {es.episode_reward:.5f}", flush=True)
+        class Q(cls):
+            def log(self):
+                pass
+        es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=256, sigma=0.02, policy_kwargs={"dims": dims},
+               agent_kwargs=dict(obs=obs, target=tgt, **akw), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22,
+               log_interval=int(os.environ.get("LOG_INTERVAL", "1")), **kw)   # > 1: the post-update rollout is folded
+        assert es._fused and es.n_workers == world
+        es.train(n_steps=6)
+        theta = torch.stack([s.theta for s in es._slots])
+        ret = torch.from_numpy(es.population_returns).to(theta.device)
+        for t in (theta, ret):
+            ref = t.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(ref, t), f"{name}: rank {rank} diverged from rank 0"
+        assert torch.isfinite(theta).all() and torch.isfinite(ret).all()
+        results[(graph, name)] = theta.clone()
+        if rank == 0:
+            print(f"{name} (graph={graph}): {world} ranks bit-identical after 6 generations; precision={es._precision}; "
+                  f"graphs cached {len(es.__dict__.get('_graphs', {}))}; episode {es.episode_reward:.5f}", flush=True)
+        del es
+for name, *_ in CASES:
+    assert torch.equal(results[("1", name)], results[("0", name)]), f"{name}: graph replay differs from eager"
+if rank == 0:
+    print("graph replay == eager on every rank", flush=True)
 dist.destroy_process_group()
