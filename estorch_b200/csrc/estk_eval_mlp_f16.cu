@@ -17,10 +17,10 @@
 //   D[obs, out] = H[obs, in] * W_s[out, in]^T
 //   A  activations H: 128 rows per CTA, fp16, K-major, 128B-swizzled, RESIDENT in shared memory
 //      across layers (8 k-blocks x 16 KB, updated in place);
-//   B  W_s formed ON THE FLY in a ring of five 16 KB slots (each CTA forms its half of the N tile;
+//   B  W_s formed ON THE FLY in a ring of six 16 KB slots (each CTA forms its half of the N tile;
 //      the perturbed weights never exist in global memory).  Stage k = one [128 x 64] k-block:
 //      the TMA engine lands the fp32 theta tile as two [128 x 32] halves (SWIZZLE_128B), half A in
-//      slot k mod 3 and half B in slot 3 + k mod 2; the producers read both, add s*sigma*eps (noise
+//      slot k mod 3 and half B in slot 3 + k mod 3; the producers read both, add s*sigma*eps (noise
 //      through registers) and write the fp16 tile IN PLACE over half A -- a row of the fp16 tile
 //      occupies exactly the bytes of the same row of half A, and the eight lanes that own a row sit
 //      in one warp, so a __syncwarp separates the reads from the write.  A B slot is released by the
@@ -58,13 +58,12 @@ __device__ unsigned long long g_f16_prof[32];   // per-role cycle counters of CT
 namespace {
 
 constexpr int CG = 2;                         // CTAs per cluster = tcgen05 cta_group
-constexpr int kSlots = 5;                     // 16 KB slots of the B ring (beside 128 KB of activations):
-constexpr int kASlots = 3, kBSlots = 2;       // three hold half A / the fp16 tile, two only ever half B
+constexpr int kSlots = 6;                     // 16 KB slots of the B ring (beside 128 KB of activations):
+constexpr int kASlots = 3, kBSlots = 3;       // three hold half A / the fp16 tile, three only ever half B
 __host__ __device__ constexpr uint32_t slot_a(uint32_t k) { return k % kASlots; }
 __host__ __device__ constexpr uint32_t slot_b(uint32_t k) { return kASlots + k % kBSlots; }
 __host__ __device__ constexpr uint32_t par_a(uint32_t k) { return (k / kASlots) & 1u; }   // phase of the A slot's k-th use
 __host__ __device__ constexpr uint32_t par_b(uint32_t k) { return (k / kBSlots) & 1u; }
-constexpr int kStages = kSlots;
 constexpr int kStageBytes = kKBlockBytes;
 // TMA descriptors of the fp32 theta, one per (layer, N tile): [N x K] row-major, box [rows of the
 // tile per CTA x 32] (128 bytes), SWIZZLE_128B
@@ -135,13 +134,15 @@ __device__ __forceinline__ TaskId decode_task(const EvalF16Params& p, int task, 
 
 __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16Params p,
                                                                     const __grid_constant__ ThetaMaps maps) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Shared memory (all dynamic; the kernel declares no static __shared__, so the 1024-byte alignment the
+  // swizzled operands need is the alignment of the dynamic window itself -- checked below):
+  //   128 KB activations + 6 x 16 KB ring + 2 KB bias + barriers / layer table  =  227 KB - 0.6 KB
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sH = smem;                                    // 8 k-blocks x 16 KB
   uint8_t* sB = sH + (kMaxW / kBlockK) * kKBlockBytes;   // ring
-  float* sBias = reinterpret_cast<float*>(sB + kStages * kStageBytes);   // [2][512]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * kMaxW);
-  // slots 0..2 hold half A of a stage (theta k 0..31), then its fp16 tile; slots 3..4 only ever half B
+  float* sBias = reinterpret_cast<float*>(sB + kSlots * kStageBytes);   // [512], one layer at a time
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kMaxW);
+  // slots 0..2 hold half A of a stage (theta k 0..31), then its fp16 tile; slots 3..5 only ever half B
   uint64_t* bar_full = bars;                   // [kSlots]  fp16 tile formed in the slot           (leader's are used)
   uint64_t* bar_emptyA = bars + kSlots;        // [kSlots]  tile consumed by the MMAs (tcgen05.commit) (local)
   uint64_t* bar_emptyB = bars + 2 * kSlots;    // [kSlots]  half B read by the producers            (local)
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
   uint64_t* bar_obs = bars + 4 * kSlots + 4;   // the next task's observation image has landed   (local)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4 * kSlots + 5);
   float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kEpiWarps]
-  __shared__ Layer lay[ESTK_MAX_LAYERS];
+  Layer* lay = reinterpret_cast<Layer*>(s_loss + kEpiWarps);             // [ESTK_MAX_LAYERS]
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();          // a misaligned window would silently corrupt the swizzle
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -259,8 +261,9 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     } else if (warp == 1 && lane == 0) {
       // =================================================================== theta TMA thread
       // Walks the same (task, layer, n-tile, k-block) stage sequence as the producers.  Stage k lands
-      // in A slot k mod 3 (last used by stage k-3, freed by the MMAs' commit) and B slot 3 + k mod 2
-      // (last used by stage k-2, freed by the producers as soon as they have read it).
+      // in A slot k mod 3 (last used by stage k-3, freed by the MMAs' commit) and B slot 3 + k mod 3
+      // (last used by stage k-3 too, freed by the OTHER producer group as soon as it had read it -- so
+      // the theta of a group's next stage lands while the group is still forming its current one).
       uint32_t k = 0;
       for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
         for (int l = 0; l < L; ++l) {
@@ -342,10 +345,18 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
       for (int l = 0; l < L; ++l) {
         const long long tb0 = EPROF_T();
         const int N = lay[l].N;
-        float* bias = sBias + (l & 1) * kMaxW;
-        for (int o = etid; o < N; o += kEpiThreads)
-          bias[o] = fmaf(ssig, ld_noise1(trow + lay[l].bbase + o), __ldg(p.theta + lay[l].bbase + o));
-        named_bar_sync(1, kEpiThreads);   // publishes bias[] among the epilogue warps
+        float* bias = sBias;
+        float bnew[(kMaxW + kEpiThreads - 1) / kEpiThreads];
+#pragma unroll
+        for (int i = 0; i < (kMaxW + kEpiThreads - 1) / kEpiThreads; ++i) {
+          const int o = etid + i * kEpiThreads;
+          bnew[i] = (o < N) ? fmaf(ssig, ld_noise1(trow + lay[l].bbase + o), __ldg(p.theta + lay[l].bbase + o)) : 0.f;
+        }
+        named_bar_sync(3, kEpiThreads);   // every warp is done reading the previous layer's bias[] ...
+#pragma unroll
+        for (int i = 0; i < (kMaxW + kEpiThreads - 1) / kEpiThreads; ++i)
+          if (etid + i * kEpiThreads < N) bias[etid + i * kEpiThreads] = bnew[i];
+        named_bar_sync(1, kEpiThreads);   // ... and this layer's is published among the epilogue warps
         EPROF_ADD(12, tb0);
         const bool last = (l == L - 1);
         const bool two = N > 256;               // two N tiles: columns [0,256) and [256,N)
@@ -679,8 +690,9 @@ __global__ void __launch_bounds__(256) stage_obs_f16_kernel(const float* __restr
 }
 
 size_t f16_smem_bytes() {
-  return 1024 + (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)kSlots * kStageBytes + 2 * kMaxW * sizeof(float) +
-         (4 * kSlots + 5) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + kEpiWarps * sizeof(float) + 64;
+  return (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)kSlots * kStageBytes + kMaxW * sizeof(float) +
+         (4 * kSlots + 5) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + kEpiWarps * sizeof(float) +
+         ESTK_MAX_LAYERS * sizeof(Layer);
 }
 
 // ---- TMA descriptors of the fp32 theta (host side)
