@@ -30,8 +30,8 @@
 //   D  the whole layer output [128 x <=512] fp32 in TMEM (512 columns) as two N tiles.
 // Warp roles (20 warps, homogeneous warpgroups so that setmaxnreg can move registers):
 //   WG0    w0 MMA issuer (leader CTA), w1 TMEM allocator + theta TMA thread, w2-3 idle -> 40 registers
-//   WG1-2  8 epilogue warps: two per TMEM lane quarter, each half of the columns -> 112
-//   WG3-4  8 weight producers in 2 groups of 4 warps (noise one stage ahead in registers) -> 104
+//   WG1-2  8 epilogue warps: two per TMEM lane quarter, each half of the columns -> 96
+//   WG3-4  8 weight producers in 2 groups of 4 warps (noise two stages ahead in registers) -> 120
 // Epilogue schedule per layer: tile 0 is drained while tile 1's MMAs still run (they read the
 // activations, which therefore cannot be overwritten yet) -- bias, ReLU, fp16, parked as packed
 // pairs in the TMEM columns the drain itself freed; when the layer is accumulated the parked half
@@ -76,12 +76,12 @@ constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, la
 #endif
 constexpr int kProdGroups = ESTK_F16_GROUPS, kProdGroupWarps = kProdWarps / kProdGroups, kPT = 32 * kProdGroupWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;
-// 128*40 + 256*112 + 256*104 = 60416 <= 640*96 = 61440
+// 128*40 + 256*96 + 256*120 = 60416 <= 640*96 = 61440 (the producers hold two stages of noise in registers)
 #ifndef ESTK_F16_REGS_EPI
-#define ESTK_F16_REGS_EPI 112
+#define ESTK_F16_REGS_EPI 96
 #endif
 #ifndef ESTK_F16_REGS_PROD
-#define ESTK_F16_REGS_PROD 104
+#define ESTK_F16_REGS_PROD 120
 #endif
 constexpr int kRegsCtl = 40, kRegsEpi = ESTK_F16_REGS_EPI, kRegsProd = ESTK_F16_REGS_PROD;
 static_assert(128 * kRegsCtl + 256 * kRegsEpi + 256 * kRegsProd <= 640 * 96, "register pool of the CTA");
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     }
   } else if (warp < kProdWarp0) {
     // =================================================================== epilogue warps
-    setmaxnreg_inc<kRegsEpi>();
+    if constexpr (kRegsEpi > 96) setmaxnreg_inc<kRegsEpi>();      // 96 = the launch allocation (640 threads)
     const int ew = warp - kEpiWarp0;
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int half = ew >> 2;                  // which half of the columns of a tile this warp drains
@@ -575,10 +575,31 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     Pos pos = {cluster_id, 0, 0, 0, lay[0].K / kBlockK};
     bool has_cur = pos.task < p.n_tasks;
     if (has_cur && pgroup) has_cur = step_pos(pos, pgroup);
-    uint4 E[kIU];
+    // The noise of a stage is loaded kDepth of this group's stages ahead (kDepth * 8 128-bit registers
+    // per thread in flight all the time): the L2 path delivers ~1 GB/s per SM per KB in flight.
+#ifndef ESTK_F16_EPS_DEPTH
+#define ESTK_F16_EPS_DEPTH 2
+#endif
+    constexpr int kDepth = ESTK_F16_EPS_DEPTH;
+    uint4 E[kDepth][kIU];
     auto load_eps = [&](const St& d, int u, uint4& e) {
       e = make_uint4(0u, 0u, 0u, 0u);
       if (d.ep && u * kRS + r0 < d.rows) e = ld_noise4u(reinterpret_cast<const uint4*>(d.ep + (size_t)u * d.k_rs));
+    };
+    // descriptor of the stage kProdGroups k-blocks after `d` / `pos` (pos always tracks the furthest stage
+    // described so far): inside the same N tile only the noise pointer and the stage index move (the
+    // common case); otherwise the full descriptor
+    auto next_desc = [&](const St& d, St& out) -> bool {
+      if (pos.kb + kProdGroups < pos.nkb) {
+        pos.kb += kProdGroups;
+        out = d;
+        out.kst = d.kst + kProdGroups;
+        if (out.ep) out.ep = d.ep + kBlockK * kProdGroups;
+        return true;
+      }
+      if (!step_pos(pos, kProdGroups)) return false;
+      describe(out, pos, d.kst + kProdGroups);
+      return true;
     };
 #ifdef ESTK_TC_PROFILE
     const bool pprof = prof && pwarp == 0;
@@ -589,25 +610,9 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
 #define PPROF_ADD(i, t0) do { (void)(t0); } while (0)
 #endif
     const long long tp0 = PPROF_T();
-    St cur = {}, nxt = {};
-    if (has_cur) {
-      describe(cur, pos, (uint32_t)pgroup);
-#pragma unroll
-      for (int u = 0; u < kIU; ++u) load_eps(cur, u, E[u]);
-    }
-    while (has_cur) {
-      // this group's next stage: kProdGroups k-blocks further -- inside the same N tile only the noise
-      // pointer and the stage index move (the common case); otherwise the full descriptor
-      bool has_nxt = true;
-      if (pos.kb + kProdGroups < pos.nkb) {
-        pos.kb += kProdGroups;
-        nxt = cur;
-        nxt.kst = cur.kst + kProdGroups;
-        if (nxt.ep) nxt.ep = cur.ep + kBlockK * kProdGroups;
-      } else {
-        has_nxt = step_pos(pos, kProdGroups);
-        if (has_nxt) describe(nxt, pos, cur.kst + kProdGroups);
-      }
+    // one stage: wait for its theta halves, form the fp16 tile in place with the noise in Ecur, refill Ecur
+    // with the noise of stage `fut` (kDepth stages ahead), publish the tile, release half B
+    auto process = [&](const St& cur, uint4 (&Ecur)[kIU], bool has_fut, const St& fut) {
       const uint32_t sa = slot_a(cur.kst), sb = slot_b(cur.kst), par = par_a(cur.kst);
       const uint32_t base_a = smem_u32(sB + sa * kStageBytes), base_b = smem_u32(sB + sb * kStageBytes);
       const uint32_t rd = hsel ? base_b : base_a;               // this thread's theta chunks live in half A or B
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
 #pragma unroll
         for (int q = 0; q < kFB; ++q) {
           const float4 t0 = ta[q], t1 = tb[q];
-          const uint4 e = E[ub + q];
+          const uint4 e = Ecur[ub + q];
           const float2 e0 = unpack_f16(e.x), e1 = unpack_f16(e.y), e2 = unpack_f16(e.z), e3 = unpack_f16(e.w);
           w[q][0] = pack_f16(fmaf(cur.sg, e0.x, t0.x), fmaf(cur.sg, e0.y, t0.y));
           w[q][1] = pack_f16(fmaf(cur.sg, e1.x, t0.z), fmaf(cur.sg, e1.y, t0.w));
@@ -643,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
         for (int q = 0; q < kFB; ++q) {
           if ((ub + q) * kRS + r0 < cur.rows)
             st_shared_v4(base_a + woff + (uint32_t)(ub + q) * (kRS * 128), w[q][0], w[q][1], w[q][2], w[q][3]);
-          if (has_nxt) load_eps(nxt, ub + q, E[ub + q]);  // the noise of this thread's next stage, a whole stage ahead
+          if (has_fut) load_eps(fut, ub + q, Ecur[ub + q]);
         }
       }
       PPROF_ADD(8, tc0);
@@ -655,8 +660,36 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar_emptyB + sb)) : "memory");   // half B is free
       }
       PPROF_ADD(9, tf0);
-      cur = nxt;
-      has_cur = has_nxt;
+    };
+    // descriptors of the current stage and the kDepth following ones; E[i] holds the noise of st[i] (st[kDepth]'s
+    // is requested while st[0] is formed, into the registers st[0] frees)
+    St st[kDepth + 1];
+    bool has[kDepth + 1];
+#pragma unroll
+    for (int i = 0; i <= kDepth; ++i) { st[i] = St{}; has[i] = false; }
+    has[0] = has_cur;
+    if (has_cur) {
+      describe(st[0], pos, (uint32_t)pgroup);
+#pragma unroll
+      for (int i = 1; i <= kDepth; ++i) has[i] = has[i - 1] && next_desc(st[i - 1], st[i]);
+#pragma unroll
+      for (int i = 0; i < kDepth; ++i)
+        if (has[i]) {
+#pragma unroll
+          for (int u = 0; u < kIU; ++u) load_eps(st[i], u, E[i][u]);
+        }
+    }
+    while (has[0]) {
+      // kDepth stages per trip so that the noise register sets are indexed statically
+#pragma unroll
+      for (int r = 0; r < kDepth; ++r) {
+        if (has[0]) {
+          process(st[0], E[r], has[kDepth], st[kDepth]);
+#pragma unroll
+          for (int i = 0; i < kDepth; ++i) { st[i] = st[i + 1]; has[i] = has[i + 1]; }
+          has[kDepth] = has[kDepth - 1] && next_desc(st[kDepth - 1], st[kDepth]);
+        }
+      }
     }
     PPROF_ADD(4, tp0);
   }

@@ -26,6 +26,6 @@ for _ in range(a.iters):
         be.eval_mlp(dims, theta, table, offs, order, pairs, 0.02, obs, tgt, ret[:pairs], ret[pairs:], precision="f16",
                     table16=tb16)
     if a.what in ("both", "grad"):
-        be.rank_grad_adam(ret, None, 1.0, 0.0, P, table, offs, order, theta, m, v, st, adam_desc(lr=0.01), ranks, None, None)
+        be.rank_grad_adam(ret, None, 1.0, 0.0, P, tb16, offs, order, theta, m, v, st, adam_desc(lr=0.01), ranks, None, None)
 torch.cuda.synchronize()
 print("done")
