@@ -30,8 +30,8 @@
 //   D  the whole layer output [128 x <=512] fp32 in TMEM (512 columns) as two N tiles.
 // Warp roles (20 warps, homogeneous warpgroups so that setmaxnreg can move registers):
 //   WG0    w0 MMA issuer (leader CTA), w1 TMEM allocator + theta TMA thread, w2-3 idle -> 40 registers
-//   WG1-2  8 epilogue warps: two per TMEM lane quarter, each half of the columns -> 96
-//   WG3-4  8 weight producers in 2 groups of 4 warps (noise two stages ahead in registers) -> 120
+//   WG1-2  8 epilogue warps: two per TMEM lane quarter, each half of the columns -> 112
+//   WG3-4  8 weight producers in 2 groups of 4 warps (noise one stage ahead in registers) -> 104
 // Epilogue schedule per layer: tile 0 is drained while tile 1's MMAs still run (they read the
 // activations, which therefore cannot be overwritten yet) -- bias, ReLU, fp16, parked as packed
 // pairs in the TMEM columns the drain itself freed; when the layer is accumulated the parked half
@@ -76,12 +76,12 @@ constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, la
 #endif
 constexpr int kProdGroups = ESTK_F16_GROUPS, kProdGroupWarps = kProdWarps / kProdGroups, kPT = 32 * kProdGroupWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;
-// 128*40 + 256*96 + 256*120 = 60416 <= 640*96 = 61440 (the producers hold two stages of noise in registers)
+// 128*40 + 256*112 + 256*104 = 60416 <= 640*96 = 61440
 #ifndef ESTK_F16_REGS_EPI
-#define ESTK_F16_REGS_EPI 96
+#define ESTK_F16_REGS_EPI 112
 #endif
 #ifndef ESTK_F16_REGS_PROD
-#define ESTK_F16_REGS_PROD 120
+#define ESTK_F16_REGS_PROD 104
 #endif
 constexpr int kRegsCtl = 40, kRegsEpi = ESTK_F16_REGS_EPI, kRegsProd = ESTK_F16_REGS_PROD;
 static_assert(128 * kRegsCtl + 256 * kRegsEpi + 256 * kRegsProd <= 640 * 96, "register pool of the CTA");
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     // The noise of a stage is loaded kDepth of this group's stages ahead (kDepth * 8 128-bit registers
     // per thread in flight all the time): the L2 path delivers ~1 GB/s per SM per KB in flight.
 #ifndef ESTK_F16_EPS_DEPTH
-#define ESTK_F16_EPS_DEPTH 2
+#define ESTK_F16_EPS_DEPTH 1     // 2 (with 96 / 120 registers) measured slower: 5.05 ms vs 3.20 ms
 #endif
     constexpr int kDepth = ESTK_F16_EPS_DEPTH;
     uint4 E[kDepth][kIU];
