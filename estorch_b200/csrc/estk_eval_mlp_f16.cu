@@ -77,6 +77,9 @@ constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, la
 constexpr int kProdGroups = ESTK_F16_GROUPS, kProdGroupWarps = kProdWarps / kProdGroups, kPT = 32 * kProdGroupWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 // 128*40 + 256*112 + 256*104 = 60416 <= 640*96 = 61440
+#ifndef ESTK_F16_WHATIF
+#define ESTK_F16_WHATIF 0        // product builds: 0 (bits select what-if ablations in triage builds)
+#endif
 #ifndef ESTK_F16_REGS_EPI
 #define ESTK_F16_REGS_EPI 112
 #endif
@@ -584,7 +587,9 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     uint4 E[kDepth][kIU];
     auto load_eps = [&](const St& d, int u, uint4& e) {
       e = make_uint4(0u, 0u, 0u, 0u);
+#if !(ESTK_F16_WHATIF & 1)      // triage builds only: bit 0 = no noise loads
       if (d.ep && u * kRS + r0 < d.rows) e = ld_noise4u(reinterpret_cast<const uint4*>(d.ep + (size_t)u * d.k_rs));
+#endif
     };
     // descriptor of the stage kProdGroups k-blocks after `d` / `pos` (pos always tracks the furthest stage
     // described so far): inside the same N tile only the noise pointer and the stage index move (the
@@ -627,10 +632,14 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
         float4 ta[kFB], tb[kFB];
 #pragma unroll
         for (int q = 0; q < kFB; ++q) {
+#if ESTK_F16_WHATIF & 2         // triage builds only: bit 1 = no theta reads from the landing slots
+          ta[q] = tb[q] = make_float4(cur.sg, 0.f, 0.f, 0.f);
+#else
           if ((ub + q) * kRS + r0 < cur.rows) {
             ta[q] = ld_shared_v4(rd + roff0 + (uint32_t)(ub + q) * (kRS * 128));
             tb[q] = ld_shared_v4(rd + roff1 + (uint32_t)(ub + q) * (kRS * 128));
           }
+#endif
         }
         uint32_t w[kFB][4];
 #pragma unroll
@@ -646,7 +655,11 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
         __syncwarp();                         // every lane has read its rows of half A before any lane overwrites them
 #pragma unroll
         for (int q = 0; q < kFB; ++q) {
+#if ESTK_F16_WHATIF & 4         // triage builds only: bit 2 = the fp16 tile is not stored (only the first word, to keep the math alive)
+          if ((ub + q) * kRS + r0 < cur.rows && (w[q][0] ^ w[q][1] ^ w[q][2] ^ w[q][3]) == 0x12345u)
+#else
           if ((ub + q) * kRS + r0 < cur.rows)
+#endif
             st_shared_v4(base_a + woff + (uint32_t)(ub + q) * (kRS * 128), w[q][0], w[q][1], w[q][2], w[q][3]);
           if (has_fut) load_eps(fut, ub + q, Ecur[ub + q]);
         }
