@@ -731,7 +731,7 @@ class ES:
                 self._obs.data_ptr(), self._tgt.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream)
 
     def _graphed_generation(self, slot):
-        """Run one fused generation: eagerly the first time a configuration is seen, then
+        """Run one fused generation: eagerly the first two times a configuration is seen, then
         captured into a CUDA graph and replayed (one launch instead of ~10 + 2 collectives;
         at 8 GPUs the host-side launch cost was 40 % of a generation)."""
         self._peek_batch()
@@ -740,18 +740,28 @@ class ES:
             return self._fused_generation(slot)
         cache = self.__dict__.setdefault("_graphs", {})
         ent = cache.get(key)
-        if ent is None:                        # first sighting: eager (also warms every lazy allocation)
-            if len(cache) >= 8:                # configurations keep changing (e.g. an lr schedule): stay eager
+        if not isinstance(ent, tuple):
+            # A configuration is captured at its THIRD sighting: the first two run eagerly (they warm every lazy
+            # allocation, and the configurations that occur once per train() call -- first / last generation --
+            # never pay for a capture, which costs tens of milliseconds)
+            if ent is None and len(cache) >= 8:    # configurations keep changing (e.g. an lr schedule): stay eager
                 return self._fused_generation(slot)
-            cache[key] = "seen"
-            return self._fused_generation(slot)
-        if ent == "seen":
+            cache[key] = (ent or 0) + 1
+            if cache[key] < 3:
+                return self._fused_generation(slot)
             try:
                 graph = torch.cuda.CUDAGraph()
                 launches0 = self._be.launches
                 pending0 = self._pending_centre
-                with torch.cuda.graph(graph, stream=self._graph_stream()):
-                    self._fused_generation(slot)
+                cur, side = torch.cuda.current_stream(self._dev), self._graph_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):   # (capture_begin/end directly: torch.cuda.graph() would also run
+                    graph.capture_begin()       #  gc.collect() + empty_cache() + a device synchronize)
+                    try:
+                        self._fused_generation(slot)
+                    finally:
+                        graph.capture_end()
+                cur.wait_stream(side)
                 ent = cache[key] = (graph, self._be.launches - launches0, self._pending_centre, self._rm_live)
                 self._pending_centre = pending0
                 self._be.launches = launches0

@@ -29,6 +29,21 @@ def main():
                  returns=es.population_returns, world=es.n_workers, pairs_local=es._pairs_local,
                  pair_begin=es._pair_begin, episode=es.episode_reward, best_reward=es.best_reward)
         return
+    if algo == "es_p8192":
+        # BASELINE config 3's population (8192 members = 4096 antithetic pairs) sharded over the ranks, small policy
+        dims = [4, 16, 2]
+        gg = torch.Generator().manual_seed(5)
+        obs, tgt = torch.randn(32, 4, generator=gg), torch.randn(32, 2, generator=gg)
+        torch.manual_seed(21)
+        es = E.ES(MLP, E.DeviceAgent, torch.optim.Adam, population_size=8192, sigma=0.02, policy_kwargs={"dims": dims},
+                  agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 14,
+                  noise_seed=3, _backend=OracleBackend())
+        es.log = lambda: None
+        es.train(n_steps=2)
+        np.savez(os.path.join(out_dir, f"rank{es.rank}.npz"), theta=es._slots[0].theta.numpy(), step=es.step,
+                 returns=es.population_returns, ranks=es._ranks.numpy(), pairs_local=es._pairs_local,
+                 pair_begin=es._pair_begin, episode=float(es.episode_reward))
+        return
     if algo in ("es_unsynced", "nsra_unsynced", "ns_hooks_unsynced"):
         # Every rank seeds torch / numpy DIFFERENTLY and nothing preloads theta: what a user's script
         # does under torchrun.  The reference keeps one master copy (estorch.py:136, :401-408, :444-456);

@@ -88,3 +88,28 @@ def test_world2_replicas_agree_without_preloaded_parameters(tmp_path, algo):
     if algo != "ns_hooks_unsynced":          # device agents are deterministic: identical returns everywhere
         np.testing.assert_array_equal(r0["returns"], r1["returns"])
         assert float(r0["episode"]) == float(r1["episode"])
+
+
+def test_world2_population_8192_sharded(tmp_path):
+    """BASELINE config 3's population size (8192 members, sigma 0.02) sharded over two ranks: 2048 pairs per
+    rank, rank-major all-gather of the returns, every rank ranks all 8192, bit-identical replicas, and the
+    same update as the single-process run up to the fp32 summation order of the all-reduced gradient."""
+    import torch
+    import estorch_b200 as E
+    from _oracle_backend import OracleBackend
+    from test_api_cpu import MLP
+    r0, r1 = _run(2, "es_p8192", tmp_path)
+    assert int(r0["pairs_local"]) == 2048 and int(r1["pair_begin"]) == 2048
+    for k in ("theta", "returns", "ranks", "episode"):
+        np.testing.assert_array_equal(r0[k], r1[k])
+    assert sorted(r0["ranks"].tolist()) == list(range(8192))
+    gg = torch.Generator().manual_seed(5)
+    obs, tgt = torch.randn(32, 4, generator=gg), torch.randn(32, 2, generator=gg)
+    torch.manual_seed(21)
+    es = E.ES(MLP, E.DeviceAgent, torch.optim.Adam, population_size=8192, sigma=0.02, policy_kwargs={"dims": [4, 16, 2]},
+              agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 14,
+              noise_seed=3, _backend=OracleBackend())
+    es.log = lambda: None
+    es.train(n_steps=2)
+    assert rel_err(r0["returns"], es.population_returns) < 1e-6     # generation 2 starts from a theta that differs in
+    assert rel_err(r0["theta"], es._slots[0].theta.numpy()) < 1e-5  # the last bits (order of the all-reduce sum)

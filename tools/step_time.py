@@ -34,6 +34,6 @@ for graph in ("1", "0"):
             e1.record(); torch.cuda.synchronize()
             out.append(f"{e0.elapsed_time(e1) / 25:.3f}@{clock().replace(', ', '/')}")
         print(f"graph={graph} log_interval={li} table=2^{log2}: ms/generation per block of 25 = {' '.join(out)}; "
-              f"graphs cached {len(es.__dict__.get('_graphs', {}))}", flush=True)
+              f"graphs cached {sum(isinstance(v, tuple) for v in es.__dict__.get('_graphs', {}).values())}", flush=True)
         del es
         torch.cuda.empty_cache()
