@@ -29,7 +29,7 @@
 //      holding a single register (measured: the L2 path needs ~1 KB in flight per GB/s and SM);
 //   D  the whole layer output [128 x <=512] fp32 in TMEM (512 columns) as two N tiles.
 // Warp roles (20 warps, homogeneous warpgroups so that setmaxnreg can move registers):
-//   WG0    w0 MMA issuer (leader CTA), w1 TMEM allocator + theta TMA thread, w2 noise L2 prefetch, w3 idle -> 40 registers
+//   WG0    w0 MMA issuer (leader CTA), w1 TMEM allocator + theta TMA thread, w2-3 idle -> 40 registers
 //   WG1-2  8 epilogue warps: two per TMEM lane quarter, each half of the columns -> 112
 //   WG3-4  8 weight producers in 2 groups of 4 warps (noise one stage ahead in registers) -> 104
 // Epilogue schedule per layer: tile 0 is drained while tile 1's MMAs still run (they read the
@@ -77,9 +77,6 @@ constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, la
 constexpr int kProdGroups = ESTK_F16_GROUPS, kProdGroupWarps = kProdWarps / kProdGroups, kPT = 32 * kProdGroupWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 // 128*40 + 256*112 + 256*104 = 60416 <= 640*96 = 61440
-#ifndef ESTK_F16_L2_PREFETCH
-#define ESTK_F16_L2_PREFETCH 8   // noise L2 prefetch distance in stages ahead of the TMA thread (0 = off)
-#endif
 #ifndef ESTK_F16_LDS_AHEAD
 #define ESTK_F16_LDS_AHEAD 1     // the theta reads of the next rows are issued before the current rows are formed
 #endif
@@ -163,7 +160,6 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4 * kSlots + 5);
   float* s_loss = reinterpret_cast<float*>(s_tmem + 2);  // [kEpiWarps]
   Layer* lay = reinterpret_cast<Layer*>(s_loss + kEpiWarps);             // [ESTK_MAX_LAYERS]
-  volatile uint32_t* s_progress = reinterpret_cast<volatile uint32_t*>(lay + ESTK_MAX_LAYERS);   // stages the TMA thread has issued
   if ((smem_u32(smem) & 1023u) != 0u) __trap();          // a misaligned window would silently corrupt the swizzle
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,7 +179,6 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     mbar_init(smem_u32(bar_h + 0), CG * kEpiWarps);
     mbar_init(smem_u32(bar_h + 1), CG * kEpiWarps);
     mbar_init(smem_u32(bar_obs), 1);
-    *s_progress = 0u;
     fence_barrier_init();
   }
   if (threadIdx.x == 32) {          // per-layer geometry, in shared memory
@@ -290,45 +285,10 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
               mbar_arrive_expect_tx(land, (uint32_t)rows * 256u);
               tma_load_2d(smem_u32(sB + sa * kStageBytes), map, kb * kBlockK, n0 + (int)cta_rank * rows, land);
               tma_load_2d(smem_u32(sB + sb * kStageBytes), map, kb * kBlockK + 32, n0 + (int)cta_rank * rows, land);
-              *s_progress = k + 1u;
             }
           }
         }
       }
-    } else if (warp == 2) {
-#if ESTK_F16_L2_PREFETCH
-      // =================================================================== noise L2 prefetch warp
-      // The producers read the noise with ordinary loads, one stage ahead (registers bound how much can be
-      // in flight).  The first sign of a pair finds its row in HBM: this warp walks the stage sequence
-      // kPfDist stages ahead of the TMA thread and pulls the [rows x 128 B] noise tile of each stage into
-      // L2, so that those loads become L2 hits.
-      constexpr int kPfDist = ESTK_F16_L2_PREFETCH;
-      uint32_t k = 0;
-      for (int task = cluster_id; task < p.n_tasks; task += n_clusters) {
-        const TaskId tk = decode_task(p, task, centre);
-        const uint16_t* trow16 = nullptr;
-        if (!tk.centre) {
-          const int j = p.order ? p.order[tk.slot] : tk.slot;
-          trow16 = p.table16 + p.offsets[j];
-        }
-        for (int l = 0; l < L; ++l) {
-          const int K = lay[l].K, N = lay[l].N;
-          for (int n0 = 0; n0 < N; n0 += 256) {
-            const int rows = min(256, N - n0) / CG;
-            for (int kb = 0; kb < K / kBlockK; ++kb, ++k) {
-              while ((int)(k - *s_progress) > kPfDist) __nanosleep(128);
-              if (trow16) {
-                const uint16_t* base = trow16 + lay[l].wbase + (int64_t)(n0 + (int)cta_rank * rows) * K + kb * kBlockK;
-                for (int r = lane; r < rows; r += 32) {
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)r * K));
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)r * K + 32));
-                }
-              }
-            }
-          }
-        }
-      }
-#endif
     }
   } else if (warp < kProdWarp0) {
     // =================================================================== epilogue warps
@@ -792,7 +752,7 @@ __global__ void __launch_bounds__(256) stage_obs_f16_kernel(const float* __restr
 size_t f16_smem_bytes() {
   return (size_t)(kMaxW / kBlockK) * kKBlockBytes + (size_t)kSlots * kStageBytes + kMaxW * sizeof(float) +
          (4 * kSlots + 5) * sizeof(uint64_t) + 2 * sizeof(uint32_t) + kEpiWarps * sizeof(float) +
-         ESTK_MAX_LAYERS * sizeof(Layer) + 16;
+         ESTK_MAX_LAYERS * sizeof(Layer);
 }
 
 // ---- TMA descriptors of the fp32 theta (host side)
