@@ -77,9 +77,6 @@ constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, la
 constexpr int kProdGroups = ESTK_F16_GROUPS, kProdGroupWarps = kProdWarps / kProdGroups, kPT = 32 * kProdGroupWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 // 128*40 + 256*112 + 256*104 = 60416 <= 640*96 = 61440
-#ifndef ESTK_F16_LDS_AHEAD
-#define ESTK_F16_LDS_AHEAD 1     // the theta reads of the next rows are issued before the current rows are formed
-#endif
 #ifndef ESTK_F16_WHATIF
 #define ESTK_F16_WHATIF 0        // product builds: 0 (bits select what-if ablations in triage builds)
 #endif
@@ -628,34 +625,26 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
       mbar_wait(smem_u32(bar_land + sa), par);                  // both theta halves of the stage have landed
       PPROF_ADD(7, tw0);
       const long long tc0 = PPROF_T();
-      // kFB rows per step; the ld.shared of step s+1 are issued before step s is formed (double-buffered
-      // registers), one __syncwarp per step, then the in-place stores and the refill of the noise registers
-      constexpr int kSteps = kIU / kFB;
-      float4 ta[2][kFB], tb[2][kFB];
-      auto lds_step = [&](int st_, float4 (&a)[kFB], float4 (&b)[kFB]) {
+      // kFB rows per step: all ld.shared of the step first (their latency overlaps), one
+      // __syncwarp, then the in-place stores and the refill of the noise registers
+#pragma unroll
+      for (int ub = 0; ub < kIU; ub += kFB) {
+        float4 ta[kFB], tb[kFB];
 #pragma unroll
         for (int q = 0; q < kFB; ++q) {
 #if ESTK_F16_WHATIF & 2         // triage builds only: bit 1 = no theta reads from the landing slots
-          a[q] = b[q] = make_float4(cur.sg, 0.f, 0.f, 0.f);
+          ta[q] = tb[q] = make_float4(cur.sg, 0.f, 0.f, 0.f);
 #else
-          if ((st_ * kFB + q) * kRS + r0 < cur.rows) {
-            a[q] = ld_shared_v4(rd + roff0 + (uint32_t)(st_ * kFB + q) * (kRS * 128));
-            b[q] = ld_shared_v4(rd + roff1 + (uint32_t)(st_ * kFB + q) * (kRS * 128));
+          if ((ub + q) * kRS + r0 < cur.rows) {
+            ta[q] = ld_shared_v4(rd + roff0 + (uint32_t)(ub + q) * (kRS * 128));
+            tb[q] = ld_shared_v4(rd + roff1 + (uint32_t)(ub + q) * (kRS * 128));
           }
 #endif
         }
-      };
-      lds_step(0, ta[0], tb[0]);
-#pragma unroll
-      for (int st_ = 0; st_ < kSteps; ++st_) {
-        const int ub = st_ * kFB;
-#if ESTK_F16_LDS_AHEAD
-        if (st_ + 1 < kSteps) lds_step(st_ + 1, ta[(st_ + 1) & 1], tb[(st_ + 1) & 1]);
-#endif
         uint32_t w[kFB][4];
 #pragma unroll
         for (int q = 0; q < kFB; ++q) {
-          const float4 t0 = ta[st_ & 1][q], t1 = tb[st_ & 1][q];
+          const float4 t0 = ta[q], t1 = tb[q];
           const uint4 e = Ecur[ub + q];
           const float2 e0 = unpack_f16(e.x), e1 = unpack_f16(e.y), e2 = unpack_f16(e.z), e3 = unpack_f16(e.w);
           w[q][0] = pack_f16(fmaf(cur.sg, e0.x, t0.x), fmaf(cur.sg, e0.y, t0.y));
@@ -674,9 +663,6 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
             st_shared_v4(base_a + woff + (uint32_t)(ub + q) * (kRS * 128), w[q][0], w[q][1], w[q][2], w[q][3]);
           if (has_fut) load_eps(fut, ub + q, Ecur[ub + q]);
         }
-#if !ESTK_F16_LDS_AHEAD
-        if (st_ + 1 < kSteps) lds_step(st_ + 1, ta[(st_ + 1) & 1], tb[(st_ + 1) & 1]);
-#endif
       }
       PPROF_ADD(8, tc0);
       const long long tf0 = PPROF_T();
