@@ -68,9 +68,13 @@ constexpr int kStageBytes = kKBlockBytes;
 // TMA descriptors of the fp32 theta, one per (layer, N tile): [N x K] row-major, box [rows of the
 // tile per CTA x 32] (128 bytes), SWIZZLE_128B
 struct ThetaMaps { CUtensorMap m[ESTK_MAX_LAYERS][2]; };
-constexpr int kCtlWarps = 4, kEpiWarps = 8, kProdWarps = 8;
+#ifndef ESTK_F16_PROD_WARPS
+#define ESTK_F16_PROD_WARPS 8
+#endif
+constexpr int kCtlWarps = 4, kEpiWarps = 8, kProdWarps = ESTK_F16_PROD_WARPS;
 constexpr int kEpiWarp0 = kCtlWarps, kProdWarp0 = kCtlWarps + kEpiWarps;
 constexpr int kThreads = 32 * (kCtlWarps + kEpiWarps + kProdWarps);   // 640, launched at 96 registers
+constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8;               // what __launch_bounds__(kThreads, 1) compiles to
 #ifndef ESTK_F16_GROUPS
 #define ESTK_F16_GROUPS 2
 #endif
@@ -86,11 +90,17 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 #ifndef ESTK_F16_REGS_PROD
 #define ESTK_F16_REGS_PROD 104
 #endif
-constexpr int kRegsCtl = 40, kRegsEpi = ESTK_F16_REGS_EPI, kRegsProd = ESTK_F16_REGS_PROD;
-static_assert(128 * kRegsCtl + 256 * kRegsEpi + 256 * kRegsProd <= 640 * 96, "register pool of the CTA");
+#ifndef ESTK_F16_REGS_CTL
+#define ESTK_F16_REGS_CTL 40
+#endif
+constexpr int kRegsCtl = ESTK_F16_REGS_CTL, kRegsEpi = ESTK_F16_REGS_EPI, kRegsProd = ESTK_F16_REGS_PROD;
+static_assert(32 * (kCtlWarps * kRegsCtl + kEpiWarps * kRegsEpi + kProdWarps * kRegsProd) <= kThreads * kLaunchRegs,
+              "register pool of the CTA");
+template <int N> __device__ __forceinline__ void set_role_regs() {     // move this warpgroup to N registers per thread
+  if constexpr (N > kLaunchRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+  else if constexpr (N < kLaunchRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
-template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 struct EvalF16Params {
   estk_mlp_desc desc;
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
 #endif
 
   if (warp < kCtlWarps) {
-    setmaxnreg_dec<kRegsCtl>();
+    set_role_regs<kRegsCtl>();
     if (warp == 0 && cta_rank == 0) {
       // =================================================================== MMA issuer
       uint32_t kst = 0, h_phase0 = 0, h_phase1 = 0;     // kst: global stage index
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     }
   } else if (warp < kProdWarp0) {
     // =================================================================== epilogue warps
-    if constexpr (kRegsEpi > 96) setmaxnreg_inc<kRegsEpi>();      // 96 = the launch allocation (640 threads)
+    set_role_regs<kRegsEpi>();
     const int ew = warp - kEpiWarp0;
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int half = ew >> 2;                  // which half of the columns of a tile this warp drains
@@ -511,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
     // slots (k < 32: slot A, k >= 32: slot B; both 128B-swizzled like the fp16 tile) + 16 bytes of
     // the noise row (fp16, a 128-bit global load issued one whole stage earlier),
     // W = rn_f16(theta + s*sigma*eps) with the sum in fp32, written over the same row of slot A.
-    setmaxnreg_inc<kRegsProd>();
+    set_role_regs<kRegsProd>();
     const int pwarp = warp - kProdWarp0;
     const int pgroup = pwarp / kProdGroupWarps;
     constexpr int kRS = kPT / 8;             // tile rows covered by one item step of the group
