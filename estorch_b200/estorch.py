@@ -333,12 +333,41 @@ class ES:
             self._pending_centre = False
             self._host_cache = {}
 
-    def _slot_state(self):
+    def _host_fetch(self):
+        """Everything log() may read -- the population's returns (and novelty) and the active slot's
+        ``estk_state`` -- in ONE device->host transfer per generation: asynchronous copies into pinned
+        buffers, a single stream synchronisation, cached until the next generation."""
         self._flush_pending_centre()
-        key = ("state", id(self._active), self.step, self._gen_token)
-        if self._host_cache.get("key") != key:
-            self._host_cache = {"key": key, "state": read_state(self._active.state)}
-        return self._host_cache["state"]
+        key = ("fetch", id(self._active), self.step, self._gen_token)
+        if self._host_cache.get("key") == key:
+            return self._host_cache
+        if getattr(self, "_rm_live", False):       # multi-GPU fused runs keep the all-gathered layout
+            cols = [self._member_order(self._returns_rm)]
+            if self._novelty is not None:
+                cols.append(self._member_order(self._novelty_rm))
+        else:
+            cols = [self._returns] if self._novelty is None else [self._returns, self._novelty]
+        dev_ret = torch.stack(cols, dim=1)
+        state = self._active.state if self._active is not None else None
+        if self._dev.type == "cuda":
+            pin = self.__dict__.setdefault("_pinned", {})
+            if pin.get("shape") != tuple(dev_ret.shape):
+                pin.update(shape=tuple(dev_ret.shape), ret=torch.empty(dev_ret.shape, dtype=torch.float32).pin_memory(),
+                           state=torch.empty(32, dtype=torch.uint8).pin_memory())
+            pin["ret"].copy_(dev_ret, non_blocking=True)
+            if state is not None:
+                pin["state"].copy_(state, non_blocking=True)
+            torch.cuda.current_stream(self._dev).synchronize()
+            host_ret = pin["ret"].numpy().copy()
+            st = read_state(pin["state"]) if state is not None else None
+        else:
+            host_ret = dev_ret.cpu().numpy()
+            st = read_state(state) if state is not None else None
+        self._host_cache = {"key": key, "returns": host_ret, "state": st}
+        return self._host_cache
+
+    def _slot_state(self):
+        return self._host_fetch()["state"]
 
     _gen_token = 0
 
@@ -395,13 +424,7 @@ class ES:
         estorch.py:441)."""
         if "_population_returns" in self.__dict__:
             return self.__dict__["_population_returns"]
-        if getattr(self, "_rm_live", False):       # multi-GPU fused runs keep the all-gathered layout
-            cols = [self._member_order(self._returns_rm)]
-            if self._novelty is not None:
-                cols.append(self._member_order(self._novelty_rm))
-        else:
-            cols = [self._returns] if self._novelty is None else [self._returns, self._novelty]
-        return torch.stack(cols, dim=1).cpu().numpy()
+        return self._host_fetch()["returns"]
 
     @population_returns.setter
     def population_returns(self, value):
