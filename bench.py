@@ -354,7 +354,9 @@ def run_ours(args, wl, rank, world, local_rank):
     torch.cuda.empty_cache()
 
     extras = None
-    if not args.no_extras and args.workload == "north_star":
+    # (single-GPU runs only: the scaling runs stay lean; the other configs at their named GPU counts are
+    #  recorded with `--workload NAME` under torchrun, see profiles/)
+    if not args.no_extras and args.workload == "north_star" and world == 1:
         extras = {}
         for name in ("cartpole", "nsra_bipedal", "config3", "atari_vbn"):
             extras[name] = run_extra(name, args, world, dev, steps=5 if name == "atari_vbn" else 20)
