@@ -662,7 +662,11 @@ __global__ void __launch_bounds__(kThreads, 1) eval_mlp_f16_kernel(const EvalF16
           w[q][2] = pack_f16(fmaf(cur.sg, e2.x, t1.x), fmaf(cur.sg, e2.y, t1.y));
           w[q][3] = pack_f16(fmaf(cur.sg, e3.x, t1.z), fmaf(cur.sg, e3.y, t1.w));
         }
+#ifdef ESTK_F16_RACECHECK_BAR   // sanitizer builds only: a CTA-scope named barrier over the group instead of the warp barrier
+        named_bar_sync(4 + pgroup, kPT);      // (compute-sanitizer racecheck does not model __syncwarp as ordering shared-memory accesses)
+#else
         __syncwarp();                         // every lane has read its rows of half A before any lane overwrites them
+#endif
 #pragma unroll
         for (int q = 0; q < kFB; ++q) {
 #if ESTK_F16_WHATIF & 4         // triage builds only: bit 2 = the fp16 tile is not stored (only the first word, to keep the math alive)
