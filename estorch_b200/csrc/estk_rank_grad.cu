@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
     const int warps = kThreads >> 5;
     const int gwarp = blockIdx.x * warps + (tid >> 5);
     const int nwarps = gridDim.x * warps;
+    // total order of numpy's argsort (estorch.py:25): NaN sorts last, NaNs among themselves by index
+    auto before = [](float a, float b) { return (a < b) || (a == a && b != b); };
+    auto same = [](float a, float b) { return (a == b) || (a != a && b != b); };
     // member index <-> position in `returns` (identity on one GPU; rank-major otherwise)
     const int pl = p.pairs / max(p.world, 1);
     auto pos_of = [&](int m) { const int sg = m / p.pairs, g = m % p.pairs; return ((g / pl) * 2 + sg) * pl + g % pl; };
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
       for (int j = lane; j < p.P; j += 32) {
         const float rj = __ldg(p.returns + j);
         const int mj = p.world > 1 ? member_of(j) : j;
-        cnt += (rj < ri) || (rj == ri && mj < i);
+        cnt += before(rj, ri) || (same(rj, ri) && mj < i);
       }
       cnt = warp_sum_i(cnt);
       int cnt2 = 0;
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
         for (int j = lane; j < p.P; j += 32) {
           const float qj = __ldg(p.novelty + j);
           const int mj = p.world > 1 ? member_of(j) : j;
-          cnt2 += (qj < qi) || (qj == qi && mj < i);
+          cnt2 += before(qj, qi) || (same(qj, qi) && mj < i);
         }
         cnt2 = warp_sum_i(cnt2);
       }

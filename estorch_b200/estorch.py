@@ -28,6 +28,7 @@ from __future__ import annotations
 import copy
 import os
 import sys
+import weakref
 from collections import OrderedDict
 from enum import Enum
 from typing import Optional
@@ -71,6 +72,38 @@ def rank_transformation(rewards):
 class _Algorithm(Enum):
     classic = 1
     novelty = 2
+
+
+_LIVE = weakref.WeakSet()      # instances that may hold CUDA graphs with captured collectives
+
+
+def _shutdown_dist():
+    """Process exit of a launcher-started rank.  A CUDA graph that captured NCCL kernels keeps a
+    reference on the communicator, and destroying the communicator first never returns
+    (profiles/r02_launcher_check.log, first run): graphs go first, then the process group."""
+    import gc
+    import torch.distributed as dist
+    for es in list(_LIVE):
+        es.__dict__.pop("_graphs", None)
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+_NVTX = os.environ.get("ESTORCH_B200_NVTX", "0") == "1"
+
+
+def _nvtx_push(name):
+    """Phase markers for nsys / ncu --nvtx (off unless ESTORCH_B200_NVTX=1; the reference has no tracing)."""
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+
+
+def _nvtx_pop():
+    if _NVTX:
+        torch.cuda.nvtx.range_pop()
 
 
 def _builtin(fn):
@@ -588,11 +621,12 @@ class ES:
     def _ensure_dist(self):
         if self.n_workers > 1:
             import torch.distributed as dist
+            _LIVE.add(self)
             if not dist.is_initialized():
                 backend = "nccl" if self._dev.type == "cuda" else "gloo"
                 dist.init_process_group(backend=backend)
                 import atexit
-                atexit.register(lambda: dist.is_initialized() and dist.destroy_process_group())
+                atexit.register(_shutdown_dist)
 
     # ------------------------------------------------------------------ fused generation
     def _adam_desc(self, optimizer):
@@ -696,6 +730,7 @@ class ES:
         else:
             R = self._returns
             ret_p, ret_m = R[pb: pb + pl], R[pairs + pb: pairs + pb + pl]
+        _nvtx_push("estk:evaluate")
         if self._is_conv:
             be.eval_conv_vbn(self._spec.n_actions, slot.theta, self._table, self._offsets, self._order, pl,
                              self.sigma, self._xref, self._obs, self._tgt, ret_p, ret_m, self._conv_scratch)
@@ -708,6 +743,8 @@ class ES:
             if folded:        # theta is still the previous update's result here (estorch.py:182-185)
                 be.track_best(slot.state, self._episode, slot.theta, slot.best_theta)
                 self._pending_centre = False
+        _nvtx_pop()
+        _nvtx_push("estk:rank_grad_adam")
         ad = self._adam_desc(slot.optimizer)
         if W == 1:
             be.rank_grad_adam(R, None, 1.0, 0.0, P, gt, self._offsets, self._order,
@@ -721,6 +758,7 @@ class ES:
                          self.n_parameters, self._grad, self._ranks, None, world=W if rm else 1)
             self._all_reduce(self._grad)
             be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
+        _nvtx_pop()
         self._best_slot = slot
         # post-update rollout (estorch.py:181-185).  It is a single 30 us task, so when nobody
         # can observe it before the next generation (no log() due, not the last generation, the

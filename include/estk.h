@@ -185,7 +185,12 @@ ESTK_API int estk_eval_mlp_center_f16(estk_ctx* ctx, const estk_mlp_desc* desc, 
                              void* stream);
 ESTK_API int estk_eval_mlp_f16_supported(const estk_mlp_desc* desc, int32_t B);
 
-/* "bf16s" (opt-in, lower precision): as estk_eval_mlp_bf16, but the weight producers read bf16 SHADOWS of
+/* NOTE on "bf16s": it evaluates F(theta16 +- sigma16 * eps16) while estk_rank_grad* weights the fp32 eps --
+ * the estimator multiplies a return by a noise vector that is not exactly the one that produced it
+ * (estorch.py:177-178 uses the same eps on both sides).  Measured at the north-star size
+ * (profiles/r02_north_star_precision.json): returns 1.6e-5 off the fp32 arithmetic, gradient 5.6e-3 (L2)
+ * off the one computed from fp32 returns.  The default mode ("f16") has neither departure.
+ * "bf16s" (opt-in, lower precision): as estk_eval_mlp_bf16, but the weight producers read bf16 SHADOWS of
  * theta and of the noise table (theta16[i] = bf16(theta[i]), table16[i] =
  * bf16(table[i]), built with estk_shadow_bf16) -- half the bytes per weight
  * element, W = bf16(theta16 + s*sigma*table16[off+i]).  Biases still come from the
@@ -240,7 +245,8 @@ ESTK_API int estk_track_best(estk_ctx* ctx, estk_state* state, const float* rewa
 /* Single-GPU fused form.  returns [P] (reward column), novelty [P] or NULL.
  * Blend row c = w_rew*c(reward) + w_nov*c(novelty) in fp32 when novelty is
  * given (ES: novelty NULL -> c(reward)).  Ranks are bit-exact vs
- * _compute_ranks on tie-free input (ties: stable by member index); centring in
+ * _compute_ranks on tie-free input (ties: stable by member index; NaN returns
+ * sort last like numpy's argsort, among themselves by index); centring in
  * fp64 then fp32 as estorch.py:17-19,:176.
  *   g = (1/P) * sum_j (c_j - c_{j+pairs}) * T[off_j : off_j+n]
  * then grad = clamp(-g), Adam(theta, m, v) in place; state->adam_step += 1.

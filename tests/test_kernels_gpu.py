@@ -300,6 +300,20 @@ def test_rank_grad_fp16_table_and_rank_major_layout(be, n, P, W):
     assert rel_err((total / P).cpu().numpy(), res["fp32"][1]) < 2e-6
 
 
+def test_rank_nan_returns_sort_last(be):
+    """A non-finite return (a diverged member) ranks like numpy's argsort ranks it (estorch.py:25): NaN last,
+    NaNs among themselves by member index; -inf / +inf at the ends."""
+    ret = np.array([0.5, np.nan, -1.0, np.inf, np.nan, -np.inf, 0.25, 0.5], dtype=np.float32)
+    table = np.random.RandomState(0).standard_normal(4096).astype(np.float32)
+    offs = orc.noise_offsets(1, 0, 0, 4, 4096, 16)
+    out = _rank_grad_adam(be, ret, table, offs, np.zeros(16, np.float32), np.zeros(16, np.float32),
+                          np.zeros(16, np.float32), 0)
+    want = np.empty(8, dtype=np.int64)
+    want[np.argsort(ret, kind="stable")] = np.arange(8)
+    np.testing.assert_array_equal(out["ranks"], want)
+    assert want[1] == 6 and want[4] == 7 and want[5] == 0 and want[3] == 5
+
+
 def test_sharded_rank_grad_equals_fused(be):
     """Multi-GPU form on one GPU: sum of per-shard raw partials -> clamp_adam
     equals the fused kernel (this is what the NCCL all-reduce computes)."""

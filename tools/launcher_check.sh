@@ -14,15 +14,21 @@ class Q(E.ES):
 es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=256, sigma=0.02, policy_kwargs={"dims": [128, 512, 288]},
        agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22)
 print("constructed", os.environ.get("RANK"), flush=True)
-es.train(n_steps=3, n_proc=2)
+es.train(n_steps=6, n_proc=2)
 torch.cuda.synchronize()
 np.save("$tmp/theta_rank%d.npy" % es.rank, es._slots[0].theta.cpu().numpy())
 print("done rank", es.rank, flush=True)
 PY
-timeout 300 python $tmp/user_script.py > $out/r02_launcher_check.log 2>&1; echo "exit $?" >> $out/r02_launcher_check.log
-python - <<PY >> $out/r02_launcher_check.log 2>&1
+: > $out/r02_launcher_check.log
+for graph in 1 0; do
+  echo "== ESTORCH_B200_GRAPH=$graph" >> $out/r02_launcher_check.log
+  s=$(date +%s)
+  ESTORCH_B200_GRAPH=$graph timeout 90 python $tmp/user_script.py >> $out/r02_launcher_check.log 2>&1
+  echo "exit $? after $(( $(date +%s) - s )) s" >> $out/r02_launcher_check.log
+  python - <<PY >> $out/r02_launcher_check.log 2>&1
 import numpy as np
 a, b = np.load("$tmp/theta_rank0.npy"), np.load("$tmp/theta_rank1.npy")
 print("ranks agree:", bool(np.array_equal(a, b)))
 PY
-grep -v "^W\|^\[W\|OMP_NUM\|^\*\*\*" $out/r02_launcher_check.log | tail -15
+done
+grep -v "^W\|^\[W\|OMP_NUM\|^\*\*\*" $out/r02_launcher_check.log | tail -30
