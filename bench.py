@@ -356,9 +356,14 @@ def run_ours(args, wl, rank, world, local_rank):
     extras = None
     # (single-GPU runs only: the scaling runs stay lean; the other configs at their named GPU counts are
     #  recorded with `--workload NAME` under torchrun, see profiles/)
-    if not args.no_extras and args.workload == "north_star" and world == 1:
+    names = ()
+    if args.extras:                       # explicit list: also under torchrun (the configs named for N GPUs)
+        names = tuple(x for x in args.extras.split(",") if x)
+    elif not args.no_extras and args.workload == "north_star" and world == 1:
+        names = ("cartpole", "nsra_bipedal", "config3", "atari_vbn")
+    if names:
         extras = {}
-        for name in ("cartpole", "nsra_bipedal", "config3", "atari_vbn"):
+        for name in names:
             extras[name] = run_extra(name, args, world, dev, steps=5 if name == "atari_vbn" else 20)
 
     if rank != 0:
@@ -494,6 +499,7 @@ def main():
     ap.add_argument("--table-log2", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--extras", default="", help="comma list of other workloads to run in the same process (any N)")
     ap.add_argument("--eval-precision", default="auto", choices=["auto", "fp32", "f16", "bf16", "bf16s"])
     args = ap.parse_args()
     # >= 5 warm-up generations on our arm: a generation configuration is captured into a CUDA graph at its third

@@ -1,19 +1,19 @@
 #!/bin/bash
-# N-GPU pass (N = number of visible GPUs): the scaling line and the BASELINE configs named for this GPU count.
+# N-GPU pass (N = number of visible GPUs), ONE process start: the scaling line plus the other BASELINE configs.
 out=gpurun_out; mkdir -p $out
 N=$(python -c "import torch; print(torch.cuda.device_count())")
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521"
-timeout 500 $TR bench.py --gpus $N --steps 100 --no-extras > $out/r02_bench_n$N.json 2> $out/r02_bench_n$N.err; tail -c 300 $out/r02_bench_n$N.err
-if [ "$N" = "8" ]; then W="config3 atari_vbn"; else W="nsra_bipedal"; fi
-for w in $W; do
-  st=100; [ $w = atari_vbn ] && st=10
-  timeout 400 $TR bench.py --gpus $N --steps $st --no-extras --workload $w > $out/r02_bench_${w}_n$N.json 2> $out/r02_bench_${w}_n$N.err
-done
+if [ "$N" = "8" ]; then X="config3,atari_vbn,nsra_bipedal"; else X="config3,nsra_bipedal"; fi
+timeout ${LIMIT:-300} $TR bench.py --gpus $N --steps 200 --extras $X > $out/r02_bench_n$N.json 2> $out/r02_bench_n$N.err
+echo "exit $?"; grep -v "^W\|^\[W\|OMP_NUM\|^\*\*\*" $out/r02_bench_n$N.err | tail -5
 python - <<PY
-import json, glob
-for f in sorted(glob.glob("$out/r02_bench_*_n$N.json") + ["$out/r02_bench_n$N.json"]):
-    try:
-        d = json.load(open(f)); print(f, round(d["value"], 1), round(d["ms_per_step"], 3), round(d["e2e"]["value"], 1), d["gpu_launches"], d.get("cuda_graph"), [(k["kernel"], round(k["ms"], 3)) for k in d.get("kernels", [])], d["clocks"])
-    except Exception as e:
-        print(f, "failed", e, open(f.replace(".json", ".err")).read()[-600:])
+import json
+try:
+    d = json.load(open("$out/r02_bench_n$N.json"))
+    print(round(d["value"], 1), round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"], 1), d["gpu_launches"], d.get("cuda_graph"),
+          [(k["kernel"], round(k["ms"], 4)) for k in d.get("kernels", [])], d["clocks"])
+    for k, v in (d.get("extra") or {}).items():
+        print(k, {a: (round(b, 2) if isinstance(b, float) else b) for a, b in v.items()})
+except Exception as e:
+    print("failed", e)
 PY
