@@ -113,3 +113,38 @@ def test_world2_population_8192_sharded(tmp_path):
     es.train(n_steps=2)
     assert rel_err(r0["returns"], es.population_returns) < 1e-6     # generation 2 starts from a theta that differs in
     assert rel_err(r0["theta"], es._slots[0].theta.numpy()) < 1e-5  # the last bits (order of the all-reduce sum)
+
+
+def test_train_n_proc_2_reexecs_under_torchrun_cpu(tmp_path):
+    """``train(n_proc=2)`` from a plain ``python script.py`` (the reference's usage: ``_fork`` re-executes the
+    calling script under mpirun, estorch.py:41-56, :305): the script is re-executed under
+    ``torch.distributed.run`` with two ranks (gloo here, the oracle stand-in as backend), both ranks finish
+    with the same parameters, rank 0 alone logs, the parent exits 0 and nobody hangs at exit."""
+    import textwrap
+    script = tmp_path / "user_script.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, numpy as np, torch
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
+        from _oracle_backend import OracleBackend
+        import estorch_b200 as E
+        from test_api_cpu import MLP
+        g = torch.Generator().manual_seed(1)
+        obs, tgt = torch.randn(32, 4, generator=g), torch.randn(32, 2, generator=g)
+        class Q(E.ES):
+            def log(self):
+                open(os.path.join({str(tmp_path)!r}, f"log_rank{{self.rank}}.txt"), "a").write(f"{{self.step}}\\n")
+        es = Q(MLP, E.DeviceAgent, torch.optim.Adam, population_size=16, sigma=0.05, policy_kwargs={{"dims": [4, 16, 2]}},
+               agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={{"lr": 0.01}}, noise_table_size=1 << 12,
+               _backend=OracleBackend())
+        es.train(n_steps=3, n_proc=2)
+        np.save(os.path.join({str(tmp_path)!r}, f"theta_rank{{es.rank}}.npy"), es._slots[0].theta.numpy())
+    """))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "ESTORCH_B200_PARENT")}
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    t0, t1 = np.load(tmp_path / "theta_rank0.npy"), np.load(tmp_path / "theta_rank1.npy")
+    np.testing.assert_array_equal(t0, t1)
+    assert (tmp_path / "log_rank0.txt").read_text().split() == ["0", "1", "2"]
+    assert not (tmp_path / "log_rank1.txt").exists()
+    # the parent (no WORLD_SIZE) never trains: it exits right after the children did
+    assert not (tmp_path / "theta_rankNone.npy").exists()
