@@ -5,7 +5,9 @@ N=$(python -c "import torch; print(torch.cuda.device_count())")
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521"
 if [ "$N" = "8" ]; then X="config3,atari_vbn,nsra_bipedal"; else X="config3,nsra_bipedal"; fi
 timeout ${LIMIT:-300} $TR bench.py --gpus $N --steps 200 --extras $X > $out/r02_bench_n$N.json 2> $out/r02_bench_n$N.err
-echo "exit $?"; grep -v "^W\|^\[W\|OMP_NUM\|^\*\*\*" $out/r02_bench_n$N.err | tail -5
+echo "exit $?"
+timeout 150 $TR tools/step_timeline.py > $out/r02_timeline_n$N.txt 2> $out/r02_timeline_n$N.err; echo "timeline exit $?"; cat $out/r02_timeline_n$N.txt; tail -3 $out/r02_timeline_n$N.err
+grep -v "^W\|^\[W\|OMP_NUM\|^\*\*\*" $out/r02_bench_n$N.err | tail -5
 python - <<PY
 import json
 try:
