@@ -27,6 +27,7 @@
 #include "estk_common.cuh"
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 namespace cg = cooperative_groups;
 
 namespace {
@@ -47,6 +48,7 @@ struct RankGradParams {
   const int32_t* order;    // [pairs_local] nullable
   int64_t n, n4;
   int CS, PS;
+  int keys_in_smem;  // phase A ranks from 64-bit keys staged in (dynamic) shared memory: P * 8 bytes
   float* cvals;    // [P] workspace
   float* partial;  // [PS * n4 * 4] workspace (PS > 1)
   int32_t* ranks_out;
@@ -132,9 +134,11 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  __shared__ float s_w[kPairTile];
-  __shared__ uint32_t s_off4[kPairTile];
+  __shared__ __align__(16) float s_w[kPairTile];
+  __shared__ __align__(16) uint32_t s_off4[kPairTile];
   __shared__ AdamScalars s_adam;
+  extern __shared__ __align__(16) unsigned long long s_key_raw[];   // [P] when p.keys_in_smem
+  uint64_t* s_key = reinterpret_cast<uint64_t*>(s_key_raw);
 
   // ---- Adam scalars (read adam_step BEFORE the first grid.sync; block 0
   //      publishes the increment after the last one, so there is no race)
@@ -161,46 +165,80 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
   }
 
   // ---- phase A: ranks.  rank_i = #{j: r_j < r_i} + #{j < i: r_j == r_i}
+  //      numpy's argsort order (estorch.py:25): NaN sorts last, NaNs among themselves by index.
   {
     const int warps = kThreads >> 5;
     const int gwarp = blockIdx.x * warps + (tid >> 5);
     const int nwarps = gridDim.x * warps;
-    // total order of numpy's argsort (estorch.py:25): NaN sorts last, NaNs among themselves by index
-    auto before = [](float a, float b) { return (a < b) || (a == a && b != b); };
-    auto same = [](float a, float b) { return (a == b) || (a != a && b != b); };
     // member index <-> position in `returns` (identity on one GPU; rank-major otherwise)
     const int pl = p.pairs / max(p.world, 1);
     auto pos_of = [&](int m) { const int sg = m / p.pairs, g = m % p.pairs; return ((g / pl) * 2 + sg) * pl + g % pl; };
     auto member_of = [&](int q) { const int r = q / (2 * pl), rem = q - r * 2 * pl; return (rem / pl) * p.pairs + r * pl + rem % pl; };
-    for (int i = gwarp; i < p.P; i += nwarps) {
-      const int pi = p.world > 1 ? pos_of(i) : i;
-      const float ri = __ldg(p.returns + pi);
-      int cnt = 0;
-      for (int j = lane; j < p.P; j += 32) {
-        const float rj = __ldg(p.returns + j);
-        const int mj = p.world > 1 ? member_of(j) : j;
-        cnt += before(rj, ri) || (same(rj, ri) && mj < i);
-      }
-      cnt = warp_sum_i(cnt);
-      int cnt2 = 0;
-      if (p.novelty) {
-        const float qi = __ldg(p.novelty + pi);
+    if (p.keys_in_smem) {
+      // Every CTA builds one 64-bit key per member in shared memory -- (order-preserving image of the
+      // fp32 value) << 32 | member index -- so that rank_i = #{j: key_j < key_i}: one shared-memory load
+      // and one 64-bit compare per (i, j), ties and the rank-major index arithmetic folded into the key.
+      auto image = [](float v) {
+        v = __fadd_rn(v, 0.f);                               // -0 -> +0 (they compare equal)
+        const uint32_t b = __float_as_uint(v);
+        return v != v ? 0xffffffffu : ((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+      };
+      auto count = [&](const float* vals, int32_t* ranks_out, bool second) {
+        __syncthreads();                                     // the previous column's keys are no longer read
+        for (int q = tid; q < p.P; q += kThreads)
+          s_key[q] = ((uint64_t)image(__ldg(vals + q)) << 32) | (uint32_t)(p.world > 1 ? member_of(q) : q);
+        __syncthreads();
+        for (int i = gwarp; i < p.P; i += nwarps) {
+          const uint64_t ki = s_key[p.world > 1 ? pos_of(i) : i];
+          int cnt = 0;
+#pragma unroll 4
+          for (int j = lane; j < p.P; j += 32) cnt += s_key[j] < ki;
+          cnt = warp_sum_i(cnt);
+          if (lane == 0) {
+            if (ranks_out) ranks_out[i] = cnt;
+            if (!second) {
+              p.cvals[i] = centre(cnt, p.P);
+            } else {
+              // estorch.py:645-646  w*c(reward) + (1-w)*c(novelty), fp32, two roundings + add
+              p.cvals[i] = __fadd_rn(__fmul_rn(p.w_rew, p.cvals[i]), __fmul_rn(p.w_nov, centre(cnt, p.P)));
+            }
+          }
+        }
+      };
+      count(p.returns, p.ranks_out, false);
+      if (p.novelty) count(p.novelty, p.ranks2_out, true);   // the same lane 0 wrote cvals[i] just above
+    } else {
+      auto before = [](float a, float b) { return (a < b) || (a == a && b != b); };
+      auto same = [](float a, float b) { return (a == b) || (a != a && b != b); };
+      for (int i = gwarp; i < p.P; i += nwarps) {
+        const int pi = p.world > 1 ? pos_of(i) : i;
+        const float ri = __ldg(p.returns + pi);
+        int cnt = 0;
         for (int j = lane; j < p.P; j += 32) {
-          const float qj = __ldg(p.novelty + j);
-          const int mj = p.world > 1 ? member_of(j) : j;
-          cnt2 += before(qj, qi) || (same(qj, qi) && mj < i);
+          const float rj = __ldg(p.returns + j);
+          cnt += before(rj, ri);
+          if (same(rj, ri)) cnt += (p.world > 1 ? member_of(j) : j) < i;   // ties are rare
         }
-        cnt2 = warp_sum_i(cnt2);
-      }
-      if (lane == 0) {
-        float c = centre(cnt, p.P);
+        cnt = warp_sum_i(cnt);
+        int cnt2 = 0;
         if (p.novelty) {
-          // estorch.py:645-646  w*c(reward) + (1-w)*c(novelty), fp32, two roundings + add
-          c = __fadd_rn(__fmul_rn(p.w_rew, c), __fmul_rn(p.w_nov, centre(cnt2, p.P)));
-          if (p.ranks2_out) p.ranks2_out[i] = cnt2;
+          const float qi = __ldg(p.novelty + pi);
+          for (int j = lane; j < p.P; j += 32) {
+            const float qj = __ldg(p.novelty + j);
+            cnt2 += before(qj, qi);
+            if (same(qj, qi)) cnt2 += (p.world > 1 ? member_of(j) : j) < i;
+          }
+          cnt2 = warp_sum_i(cnt2);
         }
-        p.cvals[i] = c;
-        if (p.ranks_out) p.ranks_out[i] = cnt;
+        if (lane == 0) {
+          float c = centre(cnt, p.P);
+          if (p.novelty) {
+            c = __fadd_rn(__fmul_rn(p.w_rew, c), __fmul_rn(p.w_nov, centre(cnt2, p.P)));
+            if (p.ranks2_out) p.ranks2_out[i] = cnt2;
+          }
+          p.cvals[i] = c;
+          if (p.ranks_out) p.ranks_out[i] = cnt;
+        }
       }
     }
   }
@@ -218,18 +256,28 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
   if constexpr (T16) {
     // fp16 table: a 128-bit load carries 8 noise values; same 16 loads in flight per thread, half the
     // bytes per pair row.  Columns are counted in vectors of 8 elements (p.n4 holds ceil(n/8) here).
-    const uint4* tab8 = reinterpret_cast<const uint4*>(p.table16);
+    // The loop is issue-bound once the bytes are halved (ncu: 60 % issue-active), so it is written for
+    // instruction count: one mad.wide.u32 per address (32-bit byte offset of the pair row + this thread's
+    // 64-bit column base), pair offsets / weights fetched four at a time, two fp32 FMAs per instruction
+    // (fma.rn.f32x2: each lane an IEEE fma, so the sums are bit-identical to the fp32-table kernel), and
+    // the number of live columns of a thread resolved once per pair tile instead of once per load.
+    const char* tabb = reinterpret_cast<const char*>(p.table16);
     for (int64_t cbase = c0; cbase < c1; cbase += (int64_t)kThreads * NC) {
       int64_t col[NC];
       bool act[NC];
-      float acc[NC][8];
+      const char* cb[NC];
+      float2 acc[NC][4];
+      int na = 0;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         col[c] = cbase + (int64_t)c * kThreads + tid;
-        act[c] = col[c] < c1;
+        act[c] = col[c] < c1;       // monotone in c: the live columns of a thread are c < na
+        na += act[c] ? 1 : 0;
+        cb[c] = tabb + (act[c] ? col[c] : c0) * 16;   // a dead lane of a live warp re-reads column c0 (one sector)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+        for (int e = 0; e < 4; ++e) acc[c][e] = make_float2(0.f, 0.f);
       }
+      const int na_w = __reduce_max_sync(0xffffffffu, na);   // warp-uniform: no divergence inside the pair loop
       for (int sbase = s0; sbase < s1; sbase += kPairTile) {
         const int cnt = min(kPairTile, s1 - sbase);
         __syncthreads();
@@ -237,46 +285,63 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
           const int jl = p.order ? p.order[sbase + t] : (sbase + t);
           const int jg = p.pair_begin + jl;
           s_w[t] = __fsub_rn(__ldcg(p.cvals + jg), __ldcg(p.cvals + jg + p.pairs));
-          s_off4[t] = (uint32_t)(p.offsets[jl] >> 3);
+          s_off4[t] = (uint32_t)(p.offsets[jl] << 1);       // BYTE offset of the row in the fp16 table (< 2^32)
         }
         __syncthreads();
         constexpr int U = LOADS / NC;
-        auto fma8 = [&](float (&a)[8], float w, const uint4& t) {
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
-          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
-          const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&t.z));
-          const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&t.w));
-          a[0] = fmaf(w, f0.x, a[0]); a[1] = fmaf(w, f0.y, a[1]); a[2] = fmaf(w, f1.x, a[2]); a[3] = fmaf(w, f1.y, a[3]);
-          a[4] = fmaf(w, f2.x, a[4]); a[5] = fmaf(w, f2.y, a[5]); a[6] = fmaf(w, f3.x, a[6]); a[7] = fmaf(w, f3.y, a[7]);
+        static_assert(U % 4 == 0, "pair offsets / weights are fetched four at a time");
+        auto row = [](const char* base, uint32_t off) {
+          uint64_t r;
+          asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"(base));
+          return reinterpret_cast<const uint4*>(r);
         };
-        int jj = 0;
-        for (; jj + U <= cnt; jj += U) {
-          uint4 t[U][NC];
+        auto fma8 = [](float2 (&a)[4], float2 w, const uint4& t) {
+          a[0] = ffma2(w, __half22float2(*reinterpret_cast<const __half2*>(&t.x)), a[0]);
+          a[1] = ffma2(w, __half22float2(*reinterpret_cast<const __half2*>(&t.y)), a[1]);
+          a[2] = ffma2(w, __half22float2(*reinterpret_cast<const __half2*>(&t.z)), a[2]);
+          a[3] = ffma2(w, __half22float2(*reinterpret_cast<const __half2*>(&t.w)), a[3]);
+        };
+        auto body = [&](auto na_tag) {
+          constexpr int NA = decltype(na_tag)::value;
+          int jj = 0;
+          for (; jj + U <= cnt; jj += U) {
+            uint4 t[U][NA];
 #pragma unroll
-          for (int u = 0; u < U; ++u)
+            for (int q = 0; q < U / 4; ++q) {
+              const uint4 o = *reinterpret_cast<const uint4*>(s_off4 + jj + 4 * q);
+              const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-            for (int c = 0; c < NC; ++c)
-              if (act[c]) t[u][c] = ld_noise4h(tab8 + (size_t)s_off4[jj + u] + col[c]);
+              for (int e = 0; e < 4; ++e)
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const float w = s_w[jj + u];
+                for (int c = 0; c < NA; ++c) t[4 * q + e][c] = ld_noise4h(row(cb[c], ov[e]));
+            }
+            __syncwarp();   // scheduling fence: all U x NA loads are issued before the first one is consumed
+                            // (bytes in flight set the rate; without it ptxas interleaves loads and FMAs)
 #pragma unroll
-            for (int c = 0; c < NC; ++c)
-              if (act[c]) fma8(acc[c], w, t[u][c]);
+            for (int q = 0; q < U / 4; ++q) {
+              const float4 w4 = *reinterpret_cast<const float4*>(s_w + jj + 4 * q);
+              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int c = 0; c < NA; ++c) fma8(acc[c], make_float2(wv[e], wv[e]), t[4 * q + e][c]);
+            }
           }
-        }
-        for (; jj < cnt; ++jj) {
-          const float w = s_w[jj];
+          for (; jj < cnt; ++jj) {
+            const float w = s_w[jj];
 #pragma unroll
-          for (int c = 0; c < NC; ++c)
-            if (act[c]) fma8(acc[c], w, ld_noise4h(tab8 + (size_t)s_off4[jj] + col[c]));
-        }
+            for (int c = 0; c < NA; ++c) fma8(acc[c], make_float2(w, w), ld_noise4h(row(cb[c], s_off4[jj])));
+          }
+        };
+        static_assert(NC <= 2, "one loop body per possible number of live columns");
+        if (na_w == NC) body(std::integral_constant<int, NC>{});
+        else if (NC > 1 && na_w == 1) body(std::integral_constant<int, 1>{});
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         if (!act[c]) continue;
-        const float4 lo = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
-        const float4 hi = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+        const float4 lo = make_float4(acc[c][0].x, acc[c][0].y, acc[c][1].x, acc[c][1].y);
+        const float4 hi = make_float4(acc[c][2].x, acc[c][2].y, acc[c][3].x, acc[c][3].y);
         if (p.PS == 1) {
           epilogue(p, adam, col[c] * 2, lo);
           if (col[c] * 8 + 4 < p.n) epilogue(p, adam, col[c] * 2 + 1, hi);
@@ -431,7 +496,16 @@ template <int NC, int T, int LOADS = 8, bool T16 = false>
 int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   constexpr int kThreads = T;
   int occ = 0;
-  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC, T, LOADS, T16>, kThreads, 0));
+  constexpr size_t kKeyBytesMax = 64 * 1024;             // P <= 8192 (BASELINE config 3); larger: global-memory path
+  static bool attr_set = false;
+  if (!attr_set) {
+    ESTK_CUDA(cudaFuncSetAttribute(rank_grad_kernel<NC, T, LOADS, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kKeyBytesMax));
+    attr_set = true;
+  }
+  const size_t key_bytes = (size_t)p.P * 8 <= kKeyBytesMax ? (size_t)p.P * 8 : 0;
+  p.keys_in_smem = key_bytes ? 1 : 0;
+  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC, T, LOADS, T16>, kThreads, key_bytes));
   if (occ < 1) {
     estk_set_error("rank_grad_kernel<%d> cannot be resident", NC);
     return ESTK_ERR_CUDA;
@@ -457,7 +531,7 @@ int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   }
   const int grid = p.CS * p.PS;
   void* args[] = {(void*)&p};
-  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC, T, LOADS, T16>, dim3(grid), dim3(kThreads), args, 0, stream));
+  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC, T, LOADS, T16>, dim3(grid), dim3(kThreads), args, key_bytes, stream));
   return ESTK_OK;
 }
 

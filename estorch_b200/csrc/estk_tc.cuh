@@ -198,17 +198,6 @@ __device__ __forceinline__ uint32_t pack_f16_relu(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_f16(uint32_t h2) {
   return __half22float2(*reinterpret_cast<const __half2*>(&h2));
 }
-// two fp32 FMAs in one instruction (sm_100 FFMA2): d = a * b + c, element-wise
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long ra, rb, rc, rd;
-  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  float2 d;
-  asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
 template <bool F16> __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
   return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
 }

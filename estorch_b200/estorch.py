@@ -374,28 +374,31 @@ class ES:
         key = ("fetch", id(self._active), self.step, self._gen_token)
         if self._host_cache.get("key") == key:
             return self._host_cache
-        if getattr(self, "_rm_live", False):       # multi-GPU fused runs keep the all-gathered layout
-            cols = [self._member_order(self._returns_rm)]
-            if self._novelty is not None:
-                cols.append(self._member_order(self._novelty_rm))
-        else:
-            cols = [self._returns] if self._novelty is None else [self._returns, self._novelty]
-        dev_ret = torch.stack(cols, dim=1)
+        rm = getattr(self, "_rm_live", False)      # multi-GPU fused runs keep the all-gathered (rank-major) layout
+        cols = [self._returns_rm if rm else self._returns]
+        if self._novelty is not None:
+            cols.append(self._novelty_rm if rm else self._novelty)
         state = self._active.state if self._active is not None else None
+        P = self.population_size
         if self._dev.type == "cuda":
+            # raw device buffers -> pinned host memory, no staging kernel; re-ordering / stacking happen on the host
             pin = self.__dict__.setdefault("_pinned", {})
-            if pin.get("shape") != tuple(dev_ret.shape):
-                pin.update(shape=tuple(dev_ret.shape), ret=torch.empty(dev_ret.shape, dtype=torch.float32).pin_memory(),
+            if pin.get("shape") != (len(cols), P):
+                pin.update(shape=(len(cols), P), ret=torch.empty(len(cols), P, dtype=torch.float32).pin_memory(),
                            state=torch.empty(32, dtype=torch.uint8).pin_memory())
-            pin["ret"].copy_(dev_ret, non_blocking=True)
+            for i, c in enumerate(cols):
+                pin["ret"][i].copy_(c.reshape(-1), non_blocking=True)
             if state is not None:
                 pin["state"].copy_(state, non_blocking=True)
             torch.cuda.current_stream(self._dev).synchronize()
-            host_ret = pin["ret"].numpy().copy()
+            raw = pin["ret"].numpy()
             st = read_state(pin["state"]) if state is not None else None
         else:
-            host_ret = dev_ret.cpu().numpy()
+            raw = torch.stack([c.reshape(-1) for c in cols]).cpu().numpy()
             st = read_state(state) if state is not None else None
+        if rm:      # [W][2][pairs/W] -> member order (all +, then all -: estorch.py:192)
+            raw = raw.reshape(len(cols), self.n_workers, 2, self._pairs_local).transpose(0, 2, 1, 3).reshape(len(cols), P)
+        host_ret = np.ascontiguousarray(raw.T)     # [P, 1] / [P, 2] like the reference's population_returns
         self._host_cache = {"key": key, "returns": host_ret, "state": st}
         return self._host_cache
 
@@ -959,9 +962,24 @@ class ES:
         """Rank 0's ``terminate()`` must stop every rank at the same generation."""
         if self.n_workers > 1:
             import torch.distributed as dist
-            flag = torch.tensor([1.0 if self._stop else 0.0], device=self._dev)
-            dist.broadcast(flag, src=0)
-            self._stop = bool(flag.item() > 0)
+            if self._dev.type != "cuda":
+                flag = torch.tensor([1.0 if self._stop else 0.0])
+                dist.broadcast(flag, src=0)
+                self._stop = bool(flag.item() > 0)
+                return
+            # pinned host word -> device word -> broadcast -> pinned host word: no allocation, one synchronisation
+            sf = self.__dict__.get("_stop_bufs")
+            if sf is None:
+                sf = self._stop_bufs = (torch.zeros(1).pin_memory(), torch.zeros(1, device=self._dev),
+                                        torch.zeros(1).pin_memory())
+            src, dev, dst = sf
+            if self.rank == 0:
+                src[0] = 1.0 if self._stop else 0.0
+                dev.copy_(src, non_blocking=True)
+            dist.broadcast(dev, src=0)
+            dst.copy_(dev, non_blocking=True)
+            torch.cuda.current_stream(self._dev).synchronize()
+            self._stop = bool(dst[0] > 0)
 
     def train(self, n_steps, n_proc=1, hwthread=False, hostfile=None):
         """Train for ``n_steps`` generations (estorch.py:272-308).
