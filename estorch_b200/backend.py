@@ -90,6 +90,7 @@ class CudaBackend:
         ctx = getattr(self, "_ctx", None)
         if ctx:
             try:
+                self.peer_close_all()
                 self.lib.estk_ctx_destroy(ctx)
             except Exception:
                 pass
@@ -284,6 +285,52 @@ class CudaBackend:
                 raise ValueError("rank-major returns (world > 1) need the fp16 table entry point")
             rc = self.lib.estk_rank_grad(*head, self._ptr(table, torch.float32, "table"), *tail)
         _capi.check(rc, "estk_rank_grad")
+        self.launches += 1
+
+    # ---------------------------------------------------------------- peer memory (CUDA IPC)
+    def peer_alloc(self, nbytes: int):
+        """Zero-filled device memory another process of this node can map: ``(pointer, 64-byte handle)``."""
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _capi.check(self.lib.estk_peer_alloc(self._ctx, int(nbytes), C.byref(ptr), handle), "estk_peer_alloc")
+        self._peer_owned = getattr(self, "_peer_owned", []) + [ptr.value]
+        return ptr.value, bytes(handle.raw)
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        _capi.check(self.lib.estk_peer_open(self._ctx, C.create_string_buffer(handle, 64), C.byref(ptr)), "estk_peer_open")
+        self._peer_mapped = getattr(self, "_peer_mapped", []) + [ptr.value]
+        return ptr.value
+
+    def peer_close_all(self):
+        """Unmap the peers' workspaces (when no kernel of this process uses them any more)."""
+        for ptr in getattr(self, "_peer_mapped", []):
+            self.lib.estk_peer_close(self._ctx, C.c_void_p(ptr))
+        self._peer_mapped = []
+
+    def peer_free_all(self):
+        """Free this process's own workspaces -- only after EVERY peer unmapped them (a barrier in between:
+        ``estorch._shutdown_dist``).  Never called from ``__del__``: 8 MB per instance wait for process exit."""
+        for ptr in getattr(self, "_peer_owned", []):
+            self.lib.estk_peer_free(self._ctx, C.c_void_p(ptr))
+        self._peer_owned = []
+
+    def xr_workspace_bytes(self, n: int) -> int:
+        return int(self.lib.estk_xr_workspace_bytes(int(n)))
+
+    def rank_grad_xr_adam(self, returns, novelty, w_rew, w_nov, P, world, rank, table16, offsets, order, pair_begin,
+                          pairs_local, peer_ptrs, theta, m, v, state, adam, ranks_out=None, ranks2_out=None,
+                          grad_out=None):
+        """Rank + partial gradient + cross-GPU sum over peer memory + Adam in one launch (estk.h).
+        ``returns`` / ``novelty`` rank-major; ``peer_ptrs`` = every rank's workspace as mapped here."""
+        arr = (C.c_void_p * world)(*[C.c_void_p(x) for x in peer_ptrs])
+        _capi.check(self.lib.estk_rank_grad_xr_adam_h(
+            self._ctx, self._ptr(returns, torch.float32, "returns"), self._ptr(novelty, torch.float32, "novelty"),
+            float(w_rew), float(w_nov), int(P), int(world), int(rank), self._ptr(table16, torch.float16, "table16"),
+            self._ptr(offsets, torch.int64, "offsets"), self._ptr(order, torch.int32, "order"), int(pair_begin),
+            int(pairs_local), theta.numel(), arr, self._ptr(theta, torch.float32, "theta"),
+            self._ptr(m, torch.float32, "m"), self._ptr(v, torch.float32, "v"), self._ptr(state, torch.uint8, "state"),
+            C.byref(adam), self._ptr(ranks_out, torch.int32, "ranks_out"), self._ptr(ranks2_out, torch.int32, "ranks2_out"),
+            self._ptr(grad_out, torch.float32, "grad_out"), self._stream()), "estk_rank_grad_xr_adam_h")
         self.launches += 1
 
     def clamp_adam(self, grad_sum, P, theta, m, v, state, adam, grad_out=None):

@@ -74,3 +74,45 @@ extern "C" int estk_ctx_info(estk_ctx* c, int* sm_count, int* cc_major, int* cc_
   if (cc_minor) *cc_minor = c->cc_minor;
   return ESTK_OK;
 }
+
+
+// ------------------------------------------------------------------ peer memory (CUDA IPC)
+// Device memory another process on the same node can map (estk.h: estk_rank_grad_xr_adam_h).
+extern "C" int estk_peer_alloc(estk_ctx* ctx, int64_t bytes, void** ptr_out, unsigned char* handle_out) {
+  ESTK_CHECK_ARG(ctx && ptr_out && handle_out && bytes > 0, "estk_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ESTK_PEER_HANDLE_BYTES, "handle size");
+  void* ptr = nullptr;
+  ESTK_CUDA(cudaMalloc(&ptr, (size_t)bytes));
+  cudaError_t e = cudaMemset(ptr, 0, (size_t)bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ptr);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(ptr);
+    estk_set_error("estk_peer_alloc: %s", cudaGetErrorString(e));
+    return ESTK_ERR_CUDA;
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *ptr_out = ptr;
+  return ESTK_OK;
+}
+
+extern "C" int estk_peer_open(estk_ctx* ctx, const unsigned char* handle, void** ptr_out) {
+  ESTK_CHECK_ARG(ctx && handle && ptr_out, "estk_peer_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  ESTK_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return ESTK_OK;
+}
+
+extern "C" int estk_peer_close(estk_ctx* ctx, void* ptr) {
+  ESTK_CHECK_ARG(ctx && ptr, "estk_peer_close: null argument");
+  ESTK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return ESTK_OK;
+}
+
+extern "C" int estk_peer_free(estk_ctx* ctx, void* ptr) {
+  ESTK_CHECK_ARG(ctx && ptr, "estk_peer_free: null argument");
+  ESTK_CUDA(cudaFree(ptr));
+  return ESTK_OK;
+}

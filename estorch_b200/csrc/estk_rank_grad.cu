@@ -62,7 +62,16 @@ struct RankGradParams {
   float* v;
   estk_state* state;
   estk_adam_desc adam;
+  // cross-GPU reduction over peer memory (estk_rank_grad_xr_adam_h): xr = world size (0: off)
+  int xr, xr_rank;
+  unsigned char* peer[ESTK_MAX_PEERS];   // every rank's workspace as mapped here; [xr_rank] is this GPU's own
 };
+
+// Layout of a cross-GPU workspace (bytes).  Flags first, then the two gradient images.
+constexpr int64_t kXrEpochOff = 0;        // uint32: launches completed by the owner (advanced by the kernel itself)
+constexpr int64_t kXrArriveOff = 256;     // uint32 arrive[ESTK_MAX_PEERS]: slot q is written by rank q only
+constexpr int64_t kXrDataOff = 4096;      // float gsum[nq * 4]  (this rank's partial sum), then float gtot[nq * 4]
+__host__ __device__ inline int64_t xr_image_bytes(int64_t n) { return ((n + 3) / 4 * 16 + 255) / 256 * 256; }
 
 struct AdamScalars {
   float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step, wd, clamp, inv_div;
@@ -91,10 +100,10 @@ __device__ __forceinline__ void adam_elem(float sum, const AdamScalars& a, float
 }
 
 __device__ __forceinline__ void epilogue(const RankGradParams& p, const AdamScalars& a,
-                                         int64_t col4, float4 s) {
+                                         int64_t col4, float4 s, bool raw) {
   const int64_t k = col4 * 4;
   const bool full = (k + 3 < p.n);
-  if (!p.fused_adam) {
+  if (raw) {
     if (full) {
       reinterpret_cast<float4*>(p.grad_sum_out)[col4] = s;
     } else {
@@ -128,7 +137,76 @@ __device__ __forceinline__ void epilogue(const RankGradParams& p, const AdamScal
   }
 }
 
-template <int NC, int T, int LOADS = 8, bool T16 = false>
+// Phase X of rank_grad_kernel (estk_rank_grad_xr_adam_h): this GPU's partial gradient sum is complete in its own
+// workspace; sum over the GPUs through peer memory, then apply the (replicated) Adam step.  Out of line on purpose:
+// its registers must not count against the streaming loop of the kernel.
+__device__ __noinline__ void xr_phase(const RankGradParams& p, const AdamScalars& adam, int kThreads) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x;
+  const int W = p.xr, me = p.xr_rank;
+  unsigned char* mine = p.peer[me];
+  const uint32_t epoch = *reinterpret_cast<volatile const uint32_t*>(mine + kXrEpochOff);   // block 0 advances it
+  const int64_t img = xr_image_bytes(p.n);                                                  // after the LAST grid.sync
+  const int64_t nq = (p.n + 3) / 4;
+  const int64_t gstride = (int64_t)gridDim.x * kThreads;
+  // A barrier over the GPUs.  `value` only grows (two per launch); slot q of a rank's arrive[] is written by
+  // rank q alone.  Called by every thread of the grid.
+  auto gpu_barrier = [&](uint32_t value) {
+    __threadfence_system();          // this thread's stores (local or over NVLink) are performed system-wide
+    grid.sync();
+    if (blockIdx.x == 0) {
+      if (tid < W) {
+        uint32_t* there = reinterpret_cast<uint32_t*>(p.peer[tid] + kXrArriveOff) + me;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(there), "r"(value) : "memory");
+        const uint32_t* here = reinterpret_cast<const uint32_t*>(mine + kXrArriveOff) + tid;
+        uint32_t seen;
+        const long long t0 = clock64();
+        for (;;) {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(here) : "memory");
+          if ((int32_t)(seen - value) >= 0) break;
+          if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a peer never arrived; fail instead of hanging the GPU
+        }
+      }
+      __syncthreads();
+    }
+    grid.sync();
+  };
+  gpu_barrier(2 * epoch + 1);
+  // reduce-scatter + all-gather of slice `me`: float4 columns [q0, q1); the sum runs in rank order on every GPU
+  {
+    const int64_t q0 = (int64_t)me * nq / W, q1 = (int64_t)(me + 1) * nq / W;
+    for (int64_t c = q0 + (int64_t)blockIdx.x * kThreads + tid; c < q1; c += gstride) {
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int qb = 0; qb < W; qb += 4) {          // four loads over NVLink in flight per thread
+        float4 t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (qb + e < W) {
+            const float4* src = reinterpret_cast<const float4*>(p.peer[qb + e] + kXrDataOff) + c;
+            asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(t[e].x), "=f"(t[e].y), "=f"(t[e].z), "=f"(t[e].w) : "l"(src) : "memory");
+          }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (qb + e < W) {
+            if (qb + e == 0) { sum = t[0]; continue; }
+            sum.x = __fadd_rn(sum.x, t[e].x); sum.y = __fadd_rn(sum.y, t[e].y);
+            sum.z = __fadd_rn(sum.z, t[e].z); sum.w = __fadd_rn(sum.w, t[e].w);
+          }
+      }
+      for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(p.peer[q] + kXrDataOff + img)[c] = sum;
+    }
+  }
+  gpu_barrier(2 * epoch + 2);
+  {
+    const float4* gtot = reinterpret_cast<const float4*>(mine + kXrDataOff + img);
+    for (int64_t c = (int64_t)blockIdx.x * kThreads + tid; c < nq; c += gstride)
+      epilogue(p, adam, c, __ldcg(gtot + c), false);
+  }
+  if (blockIdx.x == 0 && tid == 0) *reinterpret_cast<volatile uint32_t*>(mine + kXrEpochOff) = epoch + 1;
+}
+
+template <int NC, int T, int LOADS = 8, bool T16 = false, bool XR = false>
 __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
   constexpr int kThreads = T;
   cg::grid_group grid = cg::this_grid();
@@ -253,6 +331,7 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
   const int s0 = (int)((int64_t)ps * p.pairs_local / p.PS);
   const int s1 = (int)((int64_t)(ps + 1) * p.pairs_local / p.PS);
   const AdamScalars adam = s_adam;  // valid: written before the __syncthreads in grid.sync
+  const bool raw_out = !p.fused_adam || XR;   // phases B / C leave the raw sum in grad_sum_out
   if constexpr (T16) {
     // fp16 table: a 128-bit load carries 8 noise values; same 16 loads in flight per thread, half the
     // bytes per pair row.  Columns are counted in vectors of 8 elements (p.n4 holds ceil(n/8) here).
@@ -343,8 +422,8 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
         const float4 lo = make_float4(acc[c][0].x, acc[c][0].y, acc[c][1].x, acc[c][1].y);
         const float4 hi = make_float4(acc[c][2].x, acc[c][2].y, acc[c][3].x, acc[c][3].y);
         if (p.PS == 1) {
-          epilogue(p, adam, col[c] * 2, lo);
-          if (col[c] * 8 + 4 < p.n) epilogue(p, adam, col[c] * 2 + 1, hi);
+          epilogue(p, adam, col[c] * 2, lo, raw_out);
+          if (col[c] * 8 + 4 < p.n) epilogue(p, adam, col[c] * 2 + 1, hi, raw_out);
         } else {
           float4* part = reinterpret_cast<float4*>(p.partial) + ((int64_t)ps * p.n4 + col[c]) * 2;
           part[0] = lo; part[1] = hi;
@@ -413,7 +492,7 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
     for (int c = 0; c < NC; ++c) {
       if (!act[c]) continue;
       if (p.PS == 1) {
-        epilogue(p, adam, col[c], acc[c]);
+        epilogue(p, adam, col[c], acc[c], raw_out);
       } else {
         reinterpret_cast<float4*>(p.partial)[(int64_t)ps * p.n4 + col[c]] = acc[c];
       }
@@ -435,9 +514,12 @@ __global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
         const float4 t = __ldcg(reinterpret_cast<const float4*>(p.partial) + (int64_t)q * nq + col4);
         s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
       }
-      epilogue(p, adam, col4, s);
+      epilogue(p, adam, col4, s, raw_out);
     }
   }
+
+  // ---- phase X: sum over the GPUs through peer memory, then the replicated Adam step
+  if constexpr (XR) xr_phase(p, adam, kThreads);   // (only the XR instantiations pay for its registers)
   if (p.fused_adam && blockIdx.x == 0 && tid == 0) p.state->adam_step = adam_t;
 }
 
@@ -492,20 +574,20 @@ __global__ void __launch_bounds__(256) clamp_adam_kernel(const RankGradParams p,
   }
 }
 
-template <int NC, int T, int LOADS = 8, bool T16 = false>
+template <int NC, int T, int LOADS = 8, bool T16 = false, bool XR = false>
 int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   constexpr int kThreads = T;
   int occ = 0;
   constexpr size_t kKeyBytesMax = 64 * 1024;             // P <= 8192 (BASELINE config 3); larger: global-memory path
   static bool attr_set = false;
   if (!attr_set) {
-    ESTK_CUDA(cudaFuncSetAttribute(rank_grad_kernel<NC, T, LOADS, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ESTK_CUDA(cudaFuncSetAttribute(rank_grad_kernel<NC, T, LOADS, T16, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kKeyBytesMax));
     attr_set = true;
   }
   const size_t key_bytes = (size_t)p.P * 8 <= kKeyBytesMax ? (size_t)p.P * 8 : 0;
   p.keys_in_smem = key_bytes ? 1 : 0;
-  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC, T, LOADS, T16>, kThreads, key_bytes));
+  ESTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rank_grad_kernel<NC, T, LOADS, T16, XR>, kThreads, key_bytes));
   if (occ < 1) {
     estk_set_error("rank_grad_kernel<%d> cannot be resident", NC);
     return ESTK_ERR_CUDA;
@@ -531,7 +613,7 @@ int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   }
   const int grid = p.CS * p.PS;
   void* args[] = {(void*)&p};
-  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC, T, LOADS, T16>, dim3(grid), dim3(kThreads), args, key_bytes, stream));
+  ESTK_CUDA(cudaLaunchCooperativeKernel((void*)rank_grad_kernel<NC, T, LOADS, T16, XR>, dim3(grid), dim3(kThreads), args, key_bytes, stream));
   return ESTK_OK;
 }
 
@@ -551,6 +633,10 @@ int dispatch(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   // walk the table in lock-step, which is what makes overlapping rows hit L2.
   if (p.table16) {                     // fp16 table: columns are 8-element vectors
     p.n4 = (p.n + 7) / 8;
+    if (p.xr > 0) {
+      if (p.n4 >= (int64_t)ctx->sm_count * 512) return launch_rank_grad<2, 512, 16, true, true>(ctx, p, stream);
+      return launch_rank_grad<1, 256, 8, true, true>(ctx, p, stream);
+    }
     if (p.n4 >= (int64_t)ctx->sm_count * 512) return launch_rank_grad<2, 512, 16, true>(ctx, p, stream);
     return launch_rank_grad<1, 256, 8, true>(ctx, p, stream);
   }
@@ -648,6 +734,44 @@ extern "C" int estk_rank_grad_h(estk_ctx* ctx, const float* returns, const float
   ESTK_CHECK_ARG(table16 != nullptr, "estk_rank_grad_h: null table16");
   return rank_grad_impl(ctx, returns, novelty, w_rew, w_nov, P, world, nullptr, table16, offsets, order, pair_begin,
                         pairs_local, n, grad_sum_out, ranks_out, ranks2_out, stream);
+}
+
+extern "C" int64_t estk_xr_workspace_bytes(int64_t n) { return n > 0 ? kXrDataOff + 2 * xr_image_bytes(n) : 0; }
+
+extern "C" int estk_rank_grad_xr_adam_h(estk_ctx* ctx, const float* returns, const float* novelty,
+                                        float w_rew, float w_nov, int32_t P, int32_t world, int32_t rank,
+                                        const uint16_t* table16, const int64_t* offsets, const int32_t* order,
+                                        int32_t pair_begin, int32_t pairs_local, int64_t n,
+                                        void* const* peer_ws, float* theta, float* m, float* v,
+                                        estk_state* state, const estk_adam_desc* adam,
+                                        int32_t* ranks_out, int32_t* ranks2_out, float* grad_out, void* stream) {
+  ESTK_CHECK_ARG(table16 != nullptr, "estk_rank_grad_xr_adam_h: null table16");
+  int rc = check_common(ctx, returns, P, table16, offsets, n, "estk_rank_grad_xr_adam_h");
+  if (rc) return rc;
+  ESTK_CHECK_ARG(world >= 2 && world <= ESTK_MAX_PEERS && rank >= 0 && rank < world,
+                 "estk_rank_grad_xr_adam_h: world=%d rank=%d (2 <= world <= %d)", world, rank, ESTK_MAX_PEERS);
+  ESTK_CHECK_ARG((P / 2) % world == 0, "estk_rank_grad_xr_adam_h: world=%d does not divide %d pairs", world, P / 2);
+  ESTK_CHECK_ARG(pair_begin >= 0 && pairs_local > 0 && pair_begin + pairs_local <= P / 2,
+                 "estk_rank_grad_xr_adam_h: local pairs [%d,+%d) outside %d", pair_begin, pairs_local, P / 2);
+  ESTK_CHECK_ARG(theta && m && v && state && adam && peer_ws, "estk_rank_grad_xr_adam_h: null argument");
+  ESTK_CHECK_ARG(ESTK_ALIGNED16(theta) && ESTK_ALIGNED16(m) && ESTK_ALIGNED16(v) && (!grad_out || ESTK_ALIGNED16(grad_out)),
+                 "estk_rank_grad_xr_adam_h: theta/m/v/grad_out must be 16-byte aligned");
+  RankGradParams p = {};
+  p.returns = returns; p.novelty = novelty; p.w_rew = w_rew; p.w_nov = w_nov;
+  p.P = P; p.pairs = P / 2; p.pair_begin = pair_begin; p.pairs_local = pairs_local;
+  p.table = nullptr; p.table16 = table16; p.world = world; p.offsets = offsets; p.order = order;
+  p.n = n; p.n4 = (n + 3) / 4;
+  p.cvals = ctx->cvals; p.partial = ctx->partial;
+  p.ranks_out = ranks_out; p.ranks2_out = ranks2_out;
+  p.fused_adam = 1; p.grad_out = grad_out;
+  p.theta = theta; p.m = m; p.v = v; p.state = state; p.adam = *adam;
+  p.xr = world; p.xr_rank = rank;
+  for (int q = 0; q < world; ++q) {
+    ESTK_CHECK_ARG(peer_ws[q] && ESTK_ALIGNED16(peer_ws[q]), "estk_rank_grad_xr_adam_h: peer workspace %d null or unaligned", q);
+    p.peer[q] = static_cast<unsigned char*>(peer_ws[q]);
+  }
+  p.grad_sum_out = reinterpret_cast<float*>(p.peer[rank] + kXrDataOff);   // this rank's partial sum
+  return dispatch(ctx, p, (cudaStream_t)stream);
 }
 
 extern "C" int estk_clamp_adam(estk_ctx* ctx, const float* grad_sum, int32_t P, int64_t n,

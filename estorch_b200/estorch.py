@@ -88,7 +88,14 @@ def _shutdown_dist():
     gc.collect()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
+    backends = [es._be for es in list(_LIVE) if hasattr(es._be, "peer_close_all")]
+    for be in backends:                   # peer-memory workspaces: every rank unmaps, then every rank frees
+        be.peer_close_all()
     if dist.is_initialized():
+        if backends:
+            dist.barrier()
+        for be in backends:
+            be.peer_free_all()
         dist.destroy_process_group()
 
 
@@ -621,6 +628,42 @@ class ES:
         import torch.distributed as dist
         dist.all_gather_into_tensor(t_rm.view(-1), t_rm[self.rank].reshape(-1))
 
+    def _peer_workspaces(self):
+        """Device pointers of every rank's cross-GPU workspace as mapped in this process (``estk.h``:
+        estk_rank_grad_xr_adam_h sums the partial gradients over NVLink peer memory inside the kernel), or
+        None when peer memory is not available -- then the NCCL all-reduce path runs.  Set up once, at the
+        first fused generation, collectively: every rank takes the same decision."""
+        if "_peer_ptrs" in self.__dict__:
+            return self._peer_ptrs
+        import torch.distributed as dist
+        self._peer_ptrs = None
+        be, W = self._be, self.n_workers
+        ok = (self._dev.type == "cuda" and hasattr(be, "peer_alloc") and 2 <= W <= 16
+              and os.environ.get("ESTORCH_B200_PEER", "1") != "0")
+        mine = err = None
+        if ok:
+            try:
+                mine = be.peer_alloc(be.xr_workspace_bytes(self.n_parameters))
+            except Exception as e:      # no IPC in this container, out of memory, ...
+                err = repr(e)
+        handles = [None] * W
+        dist.all_gather_object(handles, None if mine is None else mine[1])
+        ptrs = None
+        if all(h is not None for h in handles):
+            try:
+                ptrs = [mine[0] if r == self.rank else be.peer_open(handles[r]) for r in range(W)]
+            except Exception as e:
+                err = repr(e)
+                ptrs = None
+        flags = [None] * W
+        dist.all_gather_object(flags, ptrs is not None)
+        if all(flags):
+            self._peer_ptrs = ptrs
+        elif ok and self.rank == 0:
+            import warnings
+            warnings.warn(f"estorch_b200: NVLink peer memory unavailable ({err}); gradients are summed with NCCL")
+        return self._peer_ptrs
+
     def _ensure_dist(self):
         if self.n_workers > 1:
             import torch.distributed as dist
@@ -753,14 +796,22 @@ class ES:
             be.rank_grad_adam(R, None, 1.0, 0.0, P, gt, self._offsets, self._order,
                               slot.theta, slot.m, slot.v, slot.state, ad, self._ranks, None, self._grad)
         else:
-            if rm:
+            peers = self._peer_workspaces() if rm else None
+            if peers is not None:
+                # ONE launch: ranks, partial gradient, sum over the GPUs through NVLink peer memory, Adam
                 self._all_gather_rm(R)
+                be.rank_grad_xr_adam(R.view(-1), None, 1.0, 0.0, P, W, self.rank, gt, self._offsets, self._order,
+                                     pb, pl, peers, slot.theta, slot.m, slot.v, slot.state, ad, self._ranks, None,
+                                     self._grad)
             else:
-                self._all_gather_halves(R)
-            be.rank_grad(R.view(-1), None, 1.0, 0.0, P, gt, self._offsets, self._order, pb, pl,
-                         self.n_parameters, self._grad, self._ranks, None, world=W if rm else 1)
-            self._all_reduce(self._grad)
-            be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
+                if rm:
+                    self._all_gather_rm(R)
+                else:
+                    self._all_gather_halves(R)
+                be.rank_grad(R.view(-1), None, 1.0, 0.0, P, gt, self._offsets, self._order, pb, pl,
+                             self.n_parameters, self._grad, self._ranks, None, world=W if rm else 1)
+                self._all_reduce(self._grad)
+                be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
         _nvtx_pop()
         self._best_slot = slot
         # post-update rollout (estorch.py:181-185).  It is a single 30 us task, so when nobody
@@ -1227,16 +1278,24 @@ class NS_ES(ES):
             be.rank_grad_adam(R, N, w_rew, w_nov, P, gt, self._offsets, self._order,
                               slot.theta, slot.m, slot.v, slot.state, ad, self._ranks, self._ranks2, self._grad)
         else:
-            if rm:
+            peers = self._peer_workspaces() if rm else None
+            if peers is not None:
                 self._all_gather_rm(R)
                 self._all_gather_rm(N)
+                be.rank_grad_xr_adam(R.view(-1), N.view(-1), w_rew, w_nov, P, W, self.rank, gt, self._offsets,
+                                     self._order, pb, pl, peers, slot.theta, slot.m, slot.v, slot.state, ad,
+                                     self._ranks, self._ranks2, self._grad)
             else:
-                self._all_gather_halves(R)
-                self._all_gather_halves(N)
-            be.rank_grad(R.view(-1), N.view(-1), w_rew, w_nov, P, gt, self._offsets, self._order, pb, pl,
-                         self.n_parameters, self._grad, self._ranks, self._ranks2, world=W if rm else 1)
-            self._all_reduce(self._grad)
-            be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
+                if rm:
+                    self._all_gather_rm(R)
+                    self._all_gather_rm(N)
+                else:
+                    self._all_gather_halves(R)
+                    self._all_gather_halves(N)
+                be.rank_grad(R.view(-1), N.view(-1), w_rew, w_nov, P, gt, self._offsets, self._order, pb, pl,
+                             self.n_parameters, self._grad, self._ranks, self._ranks2, world=W if rm else 1)
+                self._all_reduce(self._grad)
+                be.clamp_adam(self._grad, P, slot.theta, slot.m, slot.v, slot.state, ad, None)
         # _after_optimize (estorch.py:427-432 / :650-662): rollout of the updated
         # policy, archive append, best tracking, NSRA schedule (host scalars)
         be.eval_mlp_center(dims, slot.theta, self._obs, self._tgt, self._episode, self._bc_center[0],

@@ -290,6 +290,40 @@ ESTK_API int estk_rank_grad_h(estk_ctx* ctx, const float* returns, const float* 
                      int32_t pair_begin, int32_t pairs_local, int64_t n,
                      float* grad_sum_out, int32_t* ranks_out, int32_t* ranks2_out, void* stream);
 
+/* ---- the same update with the cross-GPU reduction INSIDE the kernel (NVLink peer memory) ----
+ * Replaces estk_rank_grad_h -> NCCL all-reduce -> estk_clamp_adam (the reference's gather of returns
+ * on the master + one optimizer step there, estorch.py:228-245) by ONE cooperative launch per GPU:
+ *   rank + partial gradient over the local pairs -> own workspace            (as estk_rank_grad_h)
+ *   cross-GPU barrier (flags in peer memory, release/acquire at system scope)
+ *   reduce-scatter: rank r sums slice r of all `world` workspaces in rank order (loads over NVLink),
+ *   all-gather: and stores the sum into every rank's workspace (stores over NVLink)
+ *   cross-GPU barrier
+ *   negate / clamp / Adam over all n from the summed gradient (replicated: every rank applies the
+ *   same bits to its own theta / m / v, so the replicas stay bit-identical).
+ * The sum over ranks is taken in rank order 0..world-1 on every slice: deterministic and identical on
+ * all GPUs (it differs from NCCL's order by fp32 rounding only).
+ * Every rank of the job must make the same call in the same generation (like a collective).
+ *
+ * Workspaces: estk_peer_alloc gives zero-filled device memory plus a 64-byte handle that another
+ * process on the same node turns into a device pointer with estk_peer_open (CUDA IPC; the bytes of the
+ * handle travel over whatever channel the host code has, e.g. a torch.distributed all_gather_object).
+ * `peer_ws` is a HOST array of `world` device pointers -- entry r = rank r's workspace as mapped in the
+ * calling process, entry `rank` = the caller's own allocation -- each of estk_xr_workspace_bytes(n). */
+#define ESTK_MAX_PEERS 16
+#define ESTK_PEER_HANDLE_BYTES 64
+ESTK_API int64_t estk_xr_workspace_bytes(int64_t n);
+ESTK_API int estk_peer_alloc(estk_ctx* ctx, int64_t bytes, void** ptr_out, unsigned char* handle_out);
+ESTK_API int estk_peer_open(estk_ctx* ctx, const unsigned char* handle, void** ptr_out);
+ESTK_API int estk_peer_close(estk_ctx* ctx, void* ptr);
+ESTK_API int estk_peer_free(estk_ctx* ctx, void* ptr);
+ESTK_API int estk_rank_grad_xr_adam_h(estk_ctx* ctx, const float* returns, const float* novelty,
+                             float w_rew, float w_nov, int32_t P, int32_t world, int32_t rank,
+                             const uint16_t* table16, const int64_t* offsets, const int32_t* order,
+                             int32_t pair_begin, int32_t pairs_local, int64_t n,
+                             void* const* peer_ws, float* theta, float* m, float* v,
+                             estk_state* state, const estk_adam_desc* adam,
+                             int32_t* ranks_out, int32_t* ranks2_out, float* grad_out, void* stream);
+
 /* Epilogue on an all-reduced raw sum: g = grad_sum / P, negate, clamp, Adam.
  * theta/m/v NULL with grad_out set = gradient only (for non-Adam optimizers:
  * grad_out then receives clamp(-g), the tensor the reference stores in .grad). */

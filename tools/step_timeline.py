@@ -53,7 +53,8 @@ es = build()
 es.train(5)
 for name, label in (("make_offsets", "offset hash + sort"), ("eval_mlp", "evaluate (tcgen05)"),
                     ("track_best", "best tracking"), ("rank_grad", "rank + partial gradient"),
-                    ("rank_grad_adam", "rank + gradient + Adam"), ("clamp_adam", "clamp + Adam")):
+                    ("rank_grad_adam", "rank + gradient + Adam"), ("clamp_adam", "clamp + Adam"),
+                    ("rank_grad_xr_adam", "rank + gradient + NVLink sum + Adam")):
     wrap(es._be, name, label)
 wrap(es, "_all_gather_rm", "all-gather returns (in place)")
 wrap(es, "_all_reduce", "all-reduce gradient")
