@@ -431,9 +431,18 @@ def kernel_rooflines(es, wl, args, world, rank, peaks):
                                                  es._ranks, None, None))
     else:
         rmaj = gt.dtype == torch.float16
-        t_grad = timed(lambda: be.rank_grad(R.view(-1) if rmaj else es._returns, None, 1.0, 0.0, P, gt, es._offsets,
-                                            es._order, es._pair_begin, pl, n, es._grad, es._ranks, None,
-                                            world=world if rmaj else 1))
+        peers = es.__dict__.get("_peer_ptrs")
+        if peers is not None:       # the kernel the generation runs: every rank launches it here in lock-step
+            st_scratch = slot.state.clone()
+            import torch.distributed as dist
+            dist.barrier()
+            t_grad = timed(lambda: be.rank_grad_xr_adam(R.view(-1), None, 1.0, 0.0, P, world, rank, gt, es._offsets,
+                                                        es._order, es._pair_begin, pl, peers, scratch[0], scratch[1],
+                                                        scratch[2], st_scratch, ad, es._ranks, None, None))
+        else:
+            t_grad = timed(lambda: be.rank_grad(R.view(-1) if rmaj else es._returns, None, 1.0, 0.0, P, gt,
+                                                es._offsets, es._order, es._pair_begin, pl, n, es._grad, es._ranks,
+                                                None, world=world if rmaj else 1))
     # algorithmic bytes per launch on this rank (SURVEY 8d with the table's element size: the engine's
     # table entries are fp16-representable and both kernels stream the exact 16-bit copy)
     bytes_grad = tbytes * n * pl + 28 * n + 8 * P
@@ -447,7 +456,8 @@ def kernel_rooflines(es, wl, args, world, rank, peaks):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except (OSError, ValueError):
             traffic = {}
-    kname_g = ("rank_grad_adam" if world == 1 else "rank_grad") + ("_h" if tbytes == 2 else "")
+    kname_g = ("rank_grad_adam" if world == 1 else "rank_grad_xr_adam" if es.__dict__.get("_peer_ptrs") else
+               "rank_grad") + ("_h" if tbytes == 2 else "")
     tr_g = traffic.get(kname_g)
     k_grad = {"kernel": kname_g, "bound": "l2",
               "achieved": bytes_grad / t_grad / 1e6, "peak": peaks["hbm"], "unit": "GB/s",

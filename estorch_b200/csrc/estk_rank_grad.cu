@@ -69,6 +69,7 @@ struct RankGradParams {
 
 // Layout of a cross-GPU workspace (bytes).  Flags first, then the two gradient images.
 constexpr int64_t kXrEpochOff = 0;        // uint32: launches completed by the owner (advanced by the kernel itself)
+constexpr int64_t kXrCtaCountOff = 128;   // uint32: CTAs of the owner that reached the current barrier
 constexpr int64_t kXrArriveOff = 256;     // uint32 arrive[ESTK_MAX_PEERS]: slot q is written by rank q only
 constexpr int64_t kXrDataOff = 4096;      // float gsum[nq * 4]  (this rank's partial sum), then float gtot[nq * 4]
 __host__ __device__ inline int64_t xr_image_bytes(int64_t n) { return ((n + 3) / 4 * 16 + 255) / 256 * 256; }
@@ -138,10 +139,9 @@ __device__ __forceinline__ void epilogue(const RankGradParams& p, const AdamScal
 }
 
 // Phase X of rank_grad_kernel (estk_rank_grad_xr_adam_h): this GPU's partial gradient sum is complete in its own
-// workspace; sum over the GPUs through peer memory, then apply the (replicated) Adam step.  Out of line on purpose:
-// its registers must not count against the streaming loop of the kernel.
-__device__ __noinline__ void xr_phase(const RankGradParams& p, const AdamScalars& adam, int kThreads) {
-  cg::grid_group grid = cg::this_grid();
+// workspace; sum over the GPUs through peer memory, then apply the (replicated) Adam step.  Inlined into the XR
+// instantiations only (out of line it copied the 400-byte parameter block to local memory in every thread: 9 us).
+__device__ __forceinline__ void xr_phase(const RankGradParams& p, const AdamScalars& adam, int kThreads) {
   const int tid = threadIdx.x;
   const int W = p.xr, me = p.xr_rank;
   unsigned char* mine = p.peer[me];
@@ -149,29 +149,39 @@ __device__ __noinline__ void xr_phase(const RankGradParams& p, const AdamScalars
   const int64_t img = xr_image_bytes(p.n);                                                  // after the LAST grid.sync
   const int64_t nq = (p.n + 3) / 4;
   const int64_t gstride = (int64_t)gridDim.x * kThreads;
-  // A barrier over the GPUs.  `value` only grows (two per launch); slot q of a rank's arrive[] is written by
-  // rank q alone.  Called by every thread of the grid.
-  auto gpu_barrier = [&](uint32_t value) {
-    __threadfence_system();          // this thread's stores (local or over NVLink) are performed system-wide
-    grid.sync();
-    if (blockIdx.x == 0) {
-      if (tid < W) {
-        uint32_t* there = reinterpret_cast<uint32_t*>(p.peer[tid] + kXrArriveOff) + me;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(there), "r"(value) : "memory");
-        const uint32_t* here = reinterpret_cast<const uint32_t*>(mine + kXrArriveOff) + tid;
-        uint32_t seen;
-        const long long t0 = clock64();
-        for (;;) {
-          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(here) : "memory");
-          if ((int32_t)(seen - value) >= 0) break;
-          if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a peer never arrived; fail instead of hanging the GPU
+  // A barrier over the GPUs (and over the CTAs of this one), called by every thread of the grid.  `value` only
+  // grows (two per launch); slot q of a rank's arrive[] is written by rank q alone.  No grid.sync: every CTA
+  // counts itself in, the last one tells the peers, and every CTA watches this GPU's own arrive[] words.
+  uint32_t* cta_count = reinterpret_cast<uint32_t*>(mine + kXrCtaCountOff);
+  auto gpu_barrier = [&](uint32_t value, bool remote_stores) {
+    __syncthreads();                 // this CTA's stores happen-before thread 0's fence, which is cumulative over them
+    if (tid == 0) {
+      // partial sums in this GPU's own memory are visible to NVLink readers once they are in its L2 (gpu scope);
+      // stores INTO the peers' memory must have been performed there (system scope)
+      if (remote_stores) __threadfence_system(); else __threadfence();
+      if (atomicAdd(cta_count, 1u) == gridDim.x - 1) {      // every CTA of this GPU is past its stores
+        *reinterpret_cast<volatile uint32_t*>(cta_count) = 0u;   // re-arm (nobody counts again before the peers answer)
+        __threadfence_system();                               // release: fence, then relaxed flag stores
+        for (int q = 0; q < W; ++q) {
+          uint32_t* there = reinterpret_cast<uint32_t*>(p.peer[q] + kXrArriveOff) + me;
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(there), "r"(value) : "memory");
         }
       }
-      __syncthreads();
     }
-    grid.sync();
+    if (tid < W) {
+      const uint32_t* here = reinterpret_cast<const uint32_t*>(mine + kXrArriveOff) + tid;
+      uint32_t seen;
+      const long long t0 = clock64();
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(here) : "memory");
+        if ((int32_t)(seen - value) >= 0) break;
+        if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a peer never arrived; fail instead of hanging the GPU
+      }
+      __threadfence_system();        // acquire side, once
+    }
+    __syncthreads();
   };
-  gpu_barrier(2 * epoch + 1);
+  gpu_barrier(2 * epoch + 1, false);
   // reduce-scatter + all-gather of slice `me`: float4 columns [q0, q1); the sum runs in rank order on every GPU
   {
     const int64_t q0 = (int64_t)me * nq / W, q1 = (int64_t)(me + 1) * nq / W;
@@ -197,7 +207,7 @@ __device__ __noinline__ void xr_phase(const RankGradParams& p, const AdamScalars
       for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(p.peer[q] + kXrDataOff + img)[c] = sum;
     }
   }
-  gpu_barrier(2 * epoch + 2);
+  gpu_barrier(2 * epoch + 2, true);
   {
     const float4* gtot = reinterpret_cast<const float4*>(mine + kXrDataOff + img);
     for (int64_t c = (int64_t)blockIdx.x * kThreads + tid; c < nq; c += gstride)
@@ -207,7 +217,7 @@ __device__ __noinline__ void xr_phase(const RankGradParams& p, const AdamScalars
 }
 
 template <int NC, int T, int LOADS = 8, bool T16 = false, bool XR = false>
-__global__ void __launch_bounds__(T) rank_grad_kernel(const RankGradParams p) {
+__global__ void __launch_bounds__(T, T == 256 ? 3 : 1) rank_grad_kernel(const RankGradParams p) {
   constexpr int kThreads = T;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
@@ -593,6 +603,7 @@ int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
     return ESTK_ERR_CUDA;
   }
   if (occ > 1024 / kThreads) occ = 1024 / kThreads;  // <= 1024 threads x 8 x 16 B in flight per SM
+  if (kThreads == 256 && occ > 3) occ = 3;           // the same geometry (hence the same fp32 sums) with and without XR
   const int gmax = occ * ctx->sm_count;
   const int64_t n4 = p.n4;
   if (n4 >= (int64_t)ctx->sm_count * 512) {

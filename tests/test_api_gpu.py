@@ -343,6 +343,24 @@ def test_train_n_proc_2_reexecs_under_torchrun(tmp_path):
     assert (tmp_path / "log_rank0.txt").read_text().split() == ["0", "1", "2"] and not (tmp_path / "log_rank1.txt").exists()
 
 
+def test_peer_memory_gradient_sum_matches_nccl_on_2_gpus():
+    """tools/multi_gpu_check.py under torchrun on 2 GPUs: fused ES and NSRA-ES with the gradient summed inside the
+    kernel over NVLink peer memory (estk_rank_grad_xr_adam_h) and with NCCL -- replicas bit-identical across
+    ranks, CUDA-graph replay == eager launches, the two reductions equal up to the order of an fp32 sum."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, os, socket
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert "with and without peer memory" in r.stdout
+
+
 def test_config3_population_8192_one_generation():
     """BASELINE config 3 (1M-parameter MLP, population_size = 8192, sigma = 0.02) on however many GPUs this process
     has (one): a fused generation at the default precision; ranks are the permutation the oracle computes from the

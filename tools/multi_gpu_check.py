@@ -14,9 +14,9 @@ dist.init_process_group("nccl")
 results = {}
 CASES = (("ES", E.ES, [128, 512, 288], {}, {}),
          ("NSRA_ES", E.NSRA_ES, [24, 64, 64, 4], {"weight_t": 2}, {"bc_obs": 64, "bc_dim": 256}))
-for peer, graph in (("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")):
+for peer, graph in (("force", "1"), ("force", "0"), ("0", "1"), ("0", "0")):
     os.environ["ESTORCH_B200_GRAPH"] = graph
-    os.environ["ESTORCH_B200_PEER"] = peer      # 1: gradients summed over NVLink peer memory inside the kernel; 0: NCCL
+    os.environ["ESTORCH_B200_PEER"] = peer      # force: gradients summed over NVLink peer memory inside the kernel; 0: NCCL
     for name, cls, dims, kw, akw in CASES:
         g = torch.Generator().manual_seed(3)
         obs, tgt = torch.randn(256, dims[0], generator=g), torch.randn(256, dims[-1], generator=g)
@@ -30,7 +30,7 @@ for peer, graph in (("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")):
                agent_kwargs=dict(obs=obs, target=tgt, **akw), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 22,
                log_interval=int(os.environ.get("LOG_INTERVAL", "1")), **kw)   # > 1: the post-update rollout is folded
         assert es._fused and es.n_workers == world
-        es.train(n_steps=8)
+        es.train(n_steps=int(os.environ.get("N_STEPS", "8")))
         theta = torch.stack([s.theta for s in es._slots])
         ret = torch.from_numpy(es.population_returns).to(theta.device)
         for t in (theta, ret):
@@ -39,15 +39,15 @@ for peer, graph in (("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")):
             assert torch.equal(ref, t), f"{name}: rank {rank} diverged from rank 0"
         assert torch.isfinite(theta).all() and torch.isfinite(ret).all()
         results[(peer, graph, name)] = theta.clone()
-        assert (es.__dict__.get("_peer_ptrs") is not None) == (peer == "1"), "peer-memory path not taken / taken"
+        assert (es.__dict__.get("_peer_ptrs") is not None) == (peer == "force"), "peer-memory path not taken / taken"
         if rank == 0:
             print(f"{name} (peer={peer} graph={graph}): {world} ranks bit-identical after 8 generations; precision={es._precision}; "
                   f"graphs cached {sum(isinstance(v, tuple) for v in es.__dict__.get('_graphs', {}).values())}; episode {es.episode_reward:.5f}", flush=True)
         del es
 for name, *_ in CASES:
-    for peer in ("1", "0"):
+    for peer in ("force", "0"):
         assert torch.equal(results[(peer, "1", name)], results[(peer, "0", name)]), f"{name}: graph replay differs from eager"
-    a, b = results[("1", "1", name)], results[("0", "1", name)]
+    a, b = results[("force", "1", name)], results[("0", "1", name)]
     d = (a - b).abs()
     # the in-kernel sum runs in rank order, NCCL's in its own: fp32 rounding of the summed gradient, and Adam's
     # m / (sqrt(v) + eps) turns a last-bit difference of a near-zero gradient entry into up to 2 lr per step
@@ -55,7 +55,10 @@ for name, *_ in CASES:
     if rank == 0:
         print(f"{name}: peer-memory sum vs NCCL all-reduce after 8 generations: max |d theta| {float(d.max()):.3e}, "
               f"entries differing by more than 1e-5: {100 * frac:.4f} %", flush=True)
-    assert frac < 0.02 and float(d.max()) <= 2 * 0.01 * 8 + 1e-6
+    # At 2 GPUs a two-term fp32 sum has no order: the two paths must agree bit for bit.  Beyond that the sums differ
+    # in the last bit, the centred-rank transform is discontinuous (one swapped pair of ranks moves g by ~1e-3
+    # relative at P = 256) and the trajectories drift apart like two runs with different summation orders do.
+    assert float(d.max()) == 0.0 if world == 2 else float(d.max()) <= 2 * 0.01 * 8 + 1e-6
 if rank == 0:
     print("graph replay == eager on every rank, with and without peer memory", flush=True)
 dist.destroy_process_group()
