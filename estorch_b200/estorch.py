@@ -28,6 +28,7 @@ from __future__ import annotations
 import copy
 import os
 import sys
+import time
 import weakref
 from collections import OrderedDict
 from enum import Enum
@@ -72,6 +73,15 @@ def rank_transformation(rewards):
 class _Algorithm(Enum):
     classic = 1
     novelty = 2
+
+
+def _release_shm(shm, owner):
+    try:
+        shm.close()
+        if owner:
+            shm.unlink()
+    except Exception:
+        pass
 
 
 _LIVE = weakref.WeakSet()      # instances that may hold CUDA graphs with captured collectives
@@ -1012,10 +1022,63 @@ class ES:
     def _select_slot(self):
         return self._slots[0]
 
+    def _stop_channel(self):
+        """A 16-byte shared-memory segment (all ranks of a torchrun job live on one host): rank 0 publishes
+        (sequence number, stop flag) after ``log()``, the others read it -- no collective, no GPU round trip in
+        the per-generation path.  None when a rank cannot map it (then ``_sync_stop`` broadcasts)."""
+        if "_stop_shm" in self.__dict__:
+            return self._stop_shm
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self._stop_shm = None
+        name, shm = [None], None
+        if os.environ.get("ESTORCH_B200_STOP_SHM", "1") != "0":
+            try:
+                if self.rank == 0:
+                    shm = shared_memory.SharedMemory(create=True, size=16)
+                    shm.buf[:16] = bytes(16)
+                    name = [shm.name]
+            except Exception:
+                name = [None]
+        dist.broadcast_object_list(name, src=0)
+        if self.rank != 0 and name[0] is not None:
+            try:
+                shm = shared_memory.SharedMemory(name=name[0])
+                try:        # the creator unlinks it; attaching must not register a second owner (bpo-39959)
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(shm._name, "shared_memory")
+                except Exception:
+                    pass
+            except Exception:
+                shm = None
+        oks = [None] * self.n_workers
+        dist.all_gather_object(oks, shm is not None)
+        if all(oks):
+            self._stop_shm = (shm, np.ndarray((2,), dtype=np.int64, buffer=shm.buf), [0])
+            import atexit
+            atexit.register(_release_shm, shm, self.rank == 0)
+        elif shm is not None:
+            _release_shm(shm, self.rank == 0)
+        return self._stop_shm
+
     def _sync_stop(self):
         """Rank 0's ``terminate()`` must stop every rank at the same generation."""
         if self.n_workers > 1:
             import torch.distributed as dist
+            ch = self._stop_channel()
+            if ch is not None:
+                _, words, seq = ch
+                seq[0] += 1
+                if self.rank == 0:
+                    words[1] = 1 if self._stop else 0      # flag first, sequence number second (x86 keeps the order)
+                    words[0] = seq[0]
+                else:
+                    t0 = time.monotonic()
+                    while words[0] < seq[0]:
+                        if time.monotonic() - t0 > 600.0:
+                            raise RuntimeError("estorch_b200: rank 0 did not publish its stop flag within 600 s")
+                    self._stop = bool(words[1])
+                return
             if self._dev.type != "cuda":
                 flag = torch.tensor([1.0 if self._stop else 0.0])
                 dist.broadcast(flag, src=0)
