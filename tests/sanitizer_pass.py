@@ -34,5 +34,10 @@ assert np.array_equal(ranks.cpu().numpy(), orc.compute_ranks(ret.cpu().numpy()))
 part = be.zeros(n)
 be.rank_grad(ret, None, 1.0, 0.0, P, tb16, d(offs), None, 0, pairs, n, part, ranks, None, world=1)
 assert rel((part / P).cpu().numpy(), gw) < 1e-5
+# rank-major returns of a 3-GPU job (pairs_local = 1): [rank][sign][local pair] -- the same ranks, in member order
+rm = ret.view(2, pairs).t().contiguous().view(-1)
+ranks_rm = be.zeros(P, dtype=torch.int32)
+be.rank_grad(rm, None, 1.0, 0.0, P, tb16, d(offs[:1]), None, 0, 1, n, part, ranks_rm, None, world=3)
+assert torch.equal(ranks_rm, ranks)
 torch.cuda.synchronize()
 print("sanitizer_pass ok", rel(ret.cpu().numpy(), want), rel(g.cpu().numpy(), gw))

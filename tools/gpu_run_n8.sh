@@ -7,7 +7,7 @@ if [ "$N" = "8" ]; then X="config3,atari_vbn,nsra_bipedal"; else X="config3,nsra
 timeout ${LIMIT:-300} $TR bench.py --gpus $N --steps 200 --extras $X > $out/r02_bench_n$N.json 2> $out/r02_bench_n$N.err
 echo "exit $?"
 timeout 120 $TR tools/xr_check.py 2>&1 | grep "^W=\|FAILED\|iteration 0:" | sort | uniq | head -6 | tee $out/r02_xr_check_n$N.txt
-ESTORCH_B200_PEER=0 timeout 150 $TR tools/step_timeline.py > $out/r02_timeline_n${N}_nccl.txt 2> /dev/null; cat $out/r02_timeline_n${N}_nccl.txt
+[ "$N" = "8" ] && ESTORCH_B200_PEER=0 timeout 150 $TR tools/step_timeline.py > $out/r02_timeline_n${N}_nccl.txt 2> /dev/null; cat $out/r02_timeline_n${N}_nccl.txt
 timeout 150 $TR tools/step_timeline.py > $out/r02_timeline_n$N.txt 2> $out/r02_timeline_n$N.err; echo "timeline exit $?"; cat $out/r02_timeline_n$N.txt; tail -3 $out/r02_timeline_n$N.err
 grep -v "^W\|^\[W\|OMP_NUM\|^\*\*\*" $out/r02_bench_n$N.err | tail -5
 python - <<PY
