@@ -52,7 +52,8 @@ def test_fill_noise_table_matches_oracle(be):
 
 @pytest.mark.parametrize("pairs,n,table_len,pair_begin,gen", [
     (32, 4610, 1 << 15, 0, 0), (2048, 4610, 1 << 20, 0, 3), (512, 1001760, 1 << 22, 1024, 17),
-    (5, 7, 64, 0, 1), (8192, 6020, 1 << 24, 8192, 2)])
+    (5, 7, 64, 0, 1), (8192, 6020, 1 << 24, 8192, 2), (4096, 4610, 1 << 21, 0, 5), (3000, 31, 4096, 0, 2),
+    (1, 100, 1 << 12, 0, 0), (256, 1001760, 1 << 28, 1792, 9)])
 def test_make_offsets_bit_exact(be, pairs, n, table_len, pair_begin, gen):
     from estorch_b200.backend import new_state, write_state
     offs = be.alloc(pairs, dtype=torch.int64)
