@@ -7,7 +7,7 @@ for o in estk_eval_mlp_f16 estk_eval_mlp_tc estk_rank_grad estk_eval_mlp estk_ev
   f=$L/$o.o; [ -f $f ] || continue
   echo "== $o.o"
   cuobjdump -sass $f > /tmp/_sass.txt
-  for op in UTCHMMA UTCBAR LDTM STTM UTMALDG UBLKCP "SYNCS" "USETMAXREG" "LDG.E.*128" "LDG.E.*256" "LDS.128" "STS.128" "FENCE.VIEW.ASYNC" UCGABAR " HMMA\\." "FFMA" "HADD2.F32" "F2FP"; do
+  for op in UTCHMMA UTCBAR LDTM STTM UTMALDG UBLKCP "SYNCS" "USETMAXREG" "LDG.E.*128" "LDG.E.*256" "LDS.128" "STS.128" "FENCE.VIEW.ASYNC" UCGABAR " HMMA\\." "FFMA" "FFMA2" "HADD2.F32" "F2FP" "MEMBAR.*SYS" "ATOMG\|ATOM\." "LDS.64"; do
     n=$(grep -cE "$op" /tmp/_sass.txt); [ "$n" != "0" ] && printf "  %-18s %6d\n" "$op" "$n"
   done
   grep -E "Function :" /tmp/_sass.txt | sed 's/.*Function : /  kernel /' | cut -c1-150
