@@ -286,26 +286,39 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1) rank_grad_kernel(const Ra
       };
       auto count = [&](const float* vals, int64_t ws_off, int32_t* ranks_out, bool second) {
         __syncthreads();                                     // the previous column's keys are no longer read
-        for (int q = tid; q < p.P; q += kThreads) {
-          float val;
-          if constexpr (XR) {
-            if (p.xr_gather) {
-              // the all-gather of the returns, in place of an NCCL call: position q of the rank-major array belongs
-              // to rank q / (2 pl) and is read from THAT rank's workspace over NVLink (its evaluate kernels wrote
-              // it; the barrier above says they are done); block 0 also completes this GPU's own copy for the host
-              const int owner = q / (2 * pl);
-              const float* src = reinterpret_cast<const float*>(p.peer[owner] + ws_off) + q;
-              asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(val) : "l"(src) : "memory");
-              if (blockIdx.x == 0 && owner != p.xr_rank)
-                reinterpret_cast<float*>(p.peer[p.xr_rank] + ws_off)[q] = val;
-            } else {
-              val = __ldg(vals + q);
+        bool gathered = false;
+        if constexpr (XR) {
+          if (p.xr_gather) {
+            // The all-gather of the returns, in place of an NCCL call: position q of the rank-major array belongs to
+            // rank q / (2 pl) and is read from THAT rank's workspace over NVLink (its evaluate kernels wrote it; the
+            // barrier above says they are done).  Eight loads in flight per thread (one NVLink round trip per batch,
+            // not per value); block 0 also completes this GPU's own copy for the host.
+            gathered = true;
+            for (int q0 = tid; q0 < p.P; q0 += 8 * kThreads) {
+              float val[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int q = q0 + e * kThreads;
+                if (q < p.P) {
+                  const float* src = reinterpret_cast<const float*>(p.peer[q / (2 * pl)] + ws_off) + q;
+                  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(val[e]) : "l"(src));
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int q = q0 + e * kThreads;
+                if (q < p.P) {
+                  if (blockIdx.x == 0 && q / (2 * pl) != p.xr_rank)
+                    reinterpret_cast<float*>(p.peer[p.xr_rank] + ws_off)[q] = val[e];
+                  s_key[q] = ((uint64_t)image(val[e]) << 32) | (uint32_t)member_of(q);
+                }
+              }
             }
-          } else {
-            val = __ldg(vals + q);
           }
-          s_key[q] = ((uint64_t)image(val) << 32) | (uint32_t)(p.world > 1 ? member_of(q) : q);
         }
+        if (!gathered)
+          for (int q = tid; q < p.P; q += kThreads)
+            s_key[q] = ((uint64_t)image(__ldg(vals + q)) << 32) | (uint32_t)(p.world > 1 ? member_of(q) : q);
         __syncthreads();
         for (int i = gwarp; i < p.P; i += nwarps) {
           const uint64_t ki = s_key[p.world > 1 ? pos_of(i) : i];
