@@ -77,10 +77,8 @@ SIGNATURES = {
     "estk_peer_open": [_P, C.c_char_p, C.POINTER(C.c_void_p)],
     "estk_peer_close": [_P, _P],
     "estk_peer_free": [_P, _P],
-    "estk_xr_returns_offset": [],
-    "estk_xr_novelty_offset": [],
     "estk_rank_grad_xr_adam_h": [_P, _P, _P, _F32, _F32, _I32, _I32, _I32, _P, _P, _P, _I32, _I32, _I64,
-                                 C.POINTER(C.c_void_p), _I32, _P, _P, _P, _P, C.POINTER(EstkAdamDesc), _P, _P, _P, _P],
+                                 C.POINTER(C.c_void_p), _P, _P, _P, _P, C.POINTER(EstkAdamDesc), _P, _P, _P, _P],
     "estk_clamp_adam": [_P, _P, _I32, _I64, _P, _P, _P, _P, C.POINTER(EstkAdamDesc), _P, _P],
     "estk_knn_novelty": [_P, _P, _I32, _P, _I32, _I32, _I32, _P, _P],
 }
@@ -103,8 +101,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = (C.c_char_p if name == "estk_last_error" else
-                      C.c_int64 if name in ("estk_eval_conv_vbn_scratch_bytes", "estk_xr_workspace_bytes",
-                                             "estk_xr_returns_offset", "estk_xr_novelty_offset") else C.c_int)
+                      C.c_int64 if name in ("estk_eval_conv_vbn_scratch_bytes", "estk_xr_workspace_bytes") else C.c_int)
     _lib = lib
     return lib
 

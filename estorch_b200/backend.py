@@ -317,35 +317,17 @@ class CudaBackend:
     def xr_workspace_bytes(self, n: int) -> int:
         return int(self.lib.estk_xr_workspace_bytes(int(n)))
 
-    def peer_view(self, ptr: int, count: int, dtype=torch.float32):
-        """A tensor over ``count`` elements of (peer) device memory at ``ptr`` (no ownership)."""
-        class _Raw:
-            pass
-        raw = _Raw()
-        raw.__cuda_array_interface__ = {"shape": (int(count),), "typestr": {torch.float32: "<f4", torch.int32: "<i4"}[dtype],
-                                        "data": (int(ptr), False), "version": 3, "strides": None}
-        return torch.as_tensor(raw, device=self.device)
-
-    def xr_returns_views(self, own_ptr: int, world: int, pairs_local: int):
-        """The rank-major returns / novelty arrays inside this rank's own workspace (``gather`` mode)."""
-        P = 2 * world * pairs_local
-        r = self.peer_view(own_ptr + int(self.lib.estk_xr_returns_offset()), P).view(world, 2, pairs_local)
-        nv = self.peer_view(own_ptr + int(self.lib.estk_xr_novelty_offset()), P).view(world, 2, pairs_local)
-        return r, nv
-
     def rank_grad_xr_adam(self, returns, novelty, w_rew, w_nov, P, world, rank, table16, offsets, order, pair_begin,
                           pairs_local, peer_ptrs, theta, m, v, state, adam, ranks_out=None, ranks2_out=None,
-                          grad_out=None, gather=False):
+                          grad_out=None):
         """Rank + partial gradient + cross-GPU sum over peer memory + Adam in one launch (estk.h).
-        ``returns`` / ``novelty`` rank-major; ``peer_ptrs`` = every rank's workspace as mapped here.
-        ``gather``: the arrays are the ones inside this rank's workspace (``xr_returns_views``), only the own
-        block is valid, the kernel all-gathers them."""
+        ``returns`` / ``novelty`` rank-major; ``peer_ptrs`` = every rank's workspace as mapped here."""
         arr = (C.c_void_p * world)(*[C.c_void_p(x) for x in peer_ptrs])
         _capi.check(self.lib.estk_rank_grad_xr_adam_h(
             self._ctx, self._ptr(returns, torch.float32, "returns"), self._ptr(novelty, torch.float32, "novelty"),
             float(w_rew), float(w_nov), int(P), int(world), int(rank), self._ptr(table16, torch.float16, "table16"),
             self._ptr(offsets, torch.int64, "offsets"), self._ptr(order, torch.int32, "order"), int(pair_begin),
-            int(pairs_local), theta.numel(), arr, 1 if gather else 0, self._ptr(theta, torch.float32, "theta"),
+            int(pairs_local), theta.numel(), arr, self._ptr(theta, torch.float32, "theta"),
             self._ptr(m, torch.float32, "m"), self._ptr(v, torch.float32, "v"), self._ptr(state, torch.uint8, "state"),
             C.byref(adam), self._ptr(ranks_out, torch.int32, "ranks_out"), self._ptr(ranks2_out, torch.int32, "ranks2_out"),
             self._ptr(grad_out, torch.float32, "grad_out"), self._stream()), "estk_rank_grad_xr_adam_h")

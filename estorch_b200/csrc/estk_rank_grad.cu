@@ -64,7 +64,6 @@ struct RankGradParams {
   estk_adam_desc adam;
   // cross-GPU reduction over peer memory (estk_rank_grad_xr_adam_h): xr = world size (0: off)
   int xr, xr_rank;
-  int xr_gather;          // 1: returns / novelty live in the workspaces; only the own block is valid on entry
   unsigned char* peer[ESTK_MAX_PEERS];   // every rank's workspace as mapped here; [xr_rank] is this GPU's own
 };
 
@@ -72,10 +71,7 @@ struct RankGradParams {
 constexpr int64_t kXrEpochOff = 0;        // uint32: launches completed by the owner (advanced by the kernel itself)
 constexpr int64_t kXrCtaCountOff = 128;   // uint32: CTAs of the owner that reached the current barrier
 constexpr int64_t kXrArriveOff = 256;     // uint32 arrive[ESTK_MAX_PEERS]: slot q is written by rank q only
-constexpr int64_t kXrRetOff = 4096;       // float returns[ESTK_MAX_POPULATION] then novelty[ESTK_MAX_POPULATION], rank-major:
-                                          // the owner's evaluate kernels write its own block, the kernel gathers the rest
-constexpr int64_t kXrNovOff = kXrRetOff + 4ll * ESTK_MAX_POPULATION;
-constexpr int64_t kXrDataOff = kXrNovOff + 4ll * ESTK_MAX_POPULATION;   // float gsum[nq * 4] (this rank's partial sum), then gtot[nq * 4]
+constexpr int64_t kXrDataOff = 4096;      // float gsum[nq * 4]  (this rank's partial sum), then float gtot[nq * 4]
 __host__ __device__ inline int64_t xr_image_bytes(int64_t n) { return ((n + 3) / 4 * 16 + 255) / 256 * 256; }
 
 struct AdamScalars {
@@ -142,41 +138,6 @@ __device__ __forceinline__ void epilogue(const RankGradParams& p, const AdamScal
   }
 }
 
-// A barrier over the GPUs of a job (and over the CTAs of this one), called by every thread of the grid.  `value`
-// only grows (three per launch); slot q of a rank's arrive[] is written by rank q alone.  No grid.sync: every CTA
-// counts itself in, the last one tells the peers, and every CTA watches this GPU's own arrive[] words.
-__device__ __forceinline__ void xr_barrier(const RankGradParams& p, uint32_t value, bool remote_stores) {
-  const int tid = threadIdx.x, W = p.xr, me = p.xr_rank;
-  unsigned char* mine = p.peer[me];
-  uint32_t* cta_count = reinterpret_cast<uint32_t*>(mine + kXrCtaCountOff);
-  __syncthreads();                 // this CTA's stores happen-before thread 0's fence, which is cumulative over them
-  if (tid == 0) {
-    // data in this GPU's own memory is visible to NVLink readers once it is in its L2 (gpu scope); stores INTO the
-    // peers' memory must have been performed there (system scope)
-    if (remote_stores) __threadfence_system(); else __threadfence();
-    if (atomicAdd(cta_count, 1u) == gridDim.x - 1) {      // every CTA of this GPU is past its stores
-      *reinterpret_cast<volatile uint32_t*>(cta_count) = 0u;   // re-arm (nobody counts again before the peers answer)
-      __threadfence_system();                               // release: fence, then relaxed flag stores
-      for (int q = 0; q < W; ++q) {
-        uint32_t* there = reinterpret_cast<uint32_t*>(p.peer[q] + kXrArriveOff) + me;
-        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(there), "r"(value) : "memory");
-      }
-    }
-  }
-  if (tid < W) {
-    const uint32_t* here = reinterpret_cast<const uint32_t*>(mine + kXrArriveOff) + tid;
-    uint32_t seen;
-    const long long t0 = clock64();
-    for (;;) {
-      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(here) : "memory");
-      if ((int32_t)(seen - value) >= 0) break;
-      if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a peer never arrived; fail instead of hanging the GPU
-    }
-    __threadfence_system();        // acquire side, once
-  }
-  __syncthreads();
-}
-
 // Phase X of rank_grad_kernel (estk_rank_grad_xr_adam_h): this GPU's partial gradient sum is complete in its own
 // workspace; sum over the GPUs through peer memory, then apply the (replicated) Adam step.  Inlined into the XR
 // instantiations only (out of line it copied the 400-byte parameter block to local memory in every thread: 9 us).
@@ -188,7 +149,39 @@ __device__ __forceinline__ void xr_phase(const RankGradParams& p, const AdamScal
   const int64_t img = xr_image_bytes(p.n);                                                  // after the LAST grid.sync
   const int64_t nq = (p.n + 3) / 4;
   const int64_t gstride = (int64_t)gridDim.x * kThreads;
-  xr_barrier(p, 3 * epoch + 2, false);
+  // A barrier over the GPUs (and over the CTAs of this one), called by every thread of the grid.  `value` only
+  // grows (two per launch); slot q of a rank's arrive[] is written by rank q alone.  No grid.sync: every CTA
+  // counts itself in, the last one tells the peers, and every CTA watches this GPU's own arrive[] words.
+  uint32_t* cta_count = reinterpret_cast<uint32_t*>(mine + kXrCtaCountOff);
+  auto gpu_barrier = [&](uint32_t value, bool remote_stores) {
+    __syncthreads();                 // this CTA's stores happen-before thread 0's fence, which is cumulative over them
+    if (tid == 0) {
+      // partial sums in this GPU's own memory are visible to NVLink readers once they are in its L2 (gpu scope);
+      // stores INTO the peers' memory must have been performed there (system scope)
+      if (remote_stores) __threadfence_system(); else __threadfence();
+      if (atomicAdd(cta_count, 1u) == gridDim.x - 1) {      // every CTA of this GPU is past its stores
+        *reinterpret_cast<volatile uint32_t*>(cta_count) = 0u;   // re-arm (nobody counts again before the peers answer)
+        __threadfence_system();                               // release: fence, then relaxed flag stores
+        for (int q = 0; q < W; ++q) {
+          uint32_t* there = reinterpret_cast<uint32_t*>(p.peer[q] + kXrArriveOff) + me;
+          asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(there), "r"(value) : "memory");
+        }
+      }
+    }
+    if (tid < W) {
+      const uint32_t* here = reinterpret_cast<const uint32_t*>(mine + kXrArriveOff) + tid;
+      uint32_t seen;
+      const long long t0 = clock64();
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(here) : "memory");
+        if ((int32_t)(seen - value) >= 0) break;
+        if (clock64() - t0 > (20ll << 30)) __trap();   // ~10 s: a peer never arrived; fail instead of hanging the GPU
+      }
+      __threadfence_system();        // acquire side, once
+    }
+    __syncthreads();
+  };
+  gpu_barrier(2 * epoch + 1, false);
   // reduce-scatter + all-gather of slice `me`: float4 columns [q0, q1); the sum runs in rank order on every GPU
   {
     const int64_t q0 = (int64_t)me * nq / W, q1 = (int64_t)(me + 1) * nq / W;
@@ -214,7 +207,7 @@ __device__ __forceinline__ void xr_phase(const RankGradParams& p, const AdamScal
       for (int q = 0; q < W; ++q) reinterpret_cast<float4*>(p.peer[q] + kXrDataOff + img)[c] = sum;
     }
   }
-  xr_barrier(p, 3 * epoch + 3, true);
+  gpu_barrier(2 * epoch + 2, true);
   {
     const float4* gtot = reinterpret_cast<const float4*>(mine + kXrDataOff + img);
     for (int64_t c = (int64_t)blockIdx.x * kThreads + tid; c < nq; c += gstride)
@@ -269,12 +262,6 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1) rank_grad_kernel(const Ra
     const int pl = p.pairs / max(p.world, 1);
     auto pos_of = [&](int m) { const int sg = m / p.pairs, g = m % p.pairs; return ((g / pl) * 2 + sg) * pl + g % pl; };
     auto member_of = [&](int q) { const int r = q / (2 * pl), rem = q - r * 2 * pl; return (rem / pl) * p.pairs + r * pl + rem % pl; };
-    if constexpr (XR) {
-      if (p.xr_gather) {            // every rank's evaluate kernels are complete and their blocks visible
-        const uint32_t epoch = *reinterpret_cast<volatile const uint32_t*>(p.peer[p.xr_rank] + kXrEpochOff);
-        xr_barrier(p, 3 * epoch + 1, false);
-      }
-    }
     if (p.keys_in_smem) {
       // Every CTA builds one 64-bit key per member in shared memory -- (order-preserving image of the
       // fp32 value) << 32 | member index -- so that rank_i = #{j: key_j < key_i}: one shared-memory load
@@ -284,41 +271,10 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1) rank_grad_kernel(const Ra
         const uint32_t b = __float_as_uint(v);
         return v != v ? 0xffffffffu : ((b & 0x80000000u) ? ~b : (b | 0x80000000u));
       };
-      auto count = [&](const float* vals, int64_t ws_off, int32_t* ranks_out, bool second) {
+      auto count = [&](const float* vals, int32_t* ranks_out, bool second) {
         __syncthreads();                                     // the previous column's keys are no longer read
-        bool gathered = false;
-        if constexpr (XR) {
-          if (p.xr_gather) {
-            // The all-gather of the returns, in place of an NCCL call: position q of the rank-major array belongs to
-            // rank q / (2 pl) and is read from THAT rank's workspace over NVLink (its evaluate kernels wrote it; the
-            // barrier above says they are done).  Eight loads in flight per thread (one NVLink round trip per batch,
-            // not per value); block 0 also completes this GPU's own copy for the host.
-            gathered = true;
-            for (int q0 = tid; q0 < p.P; q0 += 8 * kThreads) {
-              float val[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int q = q0 + e * kThreads;
-                if (q < p.P) {
-                  const float* src = reinterpret_cast<const float*>(p.peer[q / (2 * pl)] + ws_off) + q;
-                  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(val[e]) : "l"(src));
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int q = q0 + e * kThreads;
-                if (q < p.P) {
-                  if (blockIdx.x == 0 && q / (2 * pl) != p.xr_rank)
-                    reinterpret_cast<float*>(p.peer[p.xr_rank] + ws_off)[q] = val[e];
-                  s_key[q] = ((uint64_t)image(val[e]) << 32) | (uint32_t)member_of(q);
-                }
-              }
-            }
-          }
-        }
-        if (!gathered)
-          for (int q = tid; q < p.P; q += kThreads)
-            s_key[q] = ((uint64_t)image(__ldg(vals + q)) << 32) | (uint32_t)(p.world > 1 ? member_of(q) : q);
+        for (int q = tid; q < p.P; q += kThreads)
+          s_key[q] = ((uint64_t)image(__ldg(vals + q)) << 32) | (uint32_t)(p.world > 1 ? member_of(q) : q);
         __syncthreads();
         for (int i = gwarp; i < p.P; i += nwarps) {
           const uint64_t ki = s_key[p.world > 1 ? pos_of(i) : i];
@@ -337,8 +293,8 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1) rank_grad_kernel(const Ra
           }
         }
       };
-      count(p.returns, kXrRetOff, p.ranks_out, false);
-      if (p.novelty) count(p.novelty, kXrNovOff, p.ranks2_out, true);   // the same lane 0 wrote cvals[i] just above
+      count(p.returns, p.ranks_out, false);
+      if (p.novelty) count(p.novelty, p.ranks2_out, true);   // the same lane 0 wrote cvals[i] just above
     } else {
       auto before = [](float a, float b) { return (a < b) || (a == a && b != b); };
       auto same = [](float a, float b) { return (a == b) || (a != a && b != b); };
@@ -791,20 +747,16 @@ extern "C" int estk_rank_grad_h(estk_ctx* ctx, const float* returns, const float
                         pairs_local, n, grad_sum_out, ranks_out, ranks2_out, stream);
 }
 
-extern "C" int64_t estk_xr_returns_offset(void) { return kXrRetOff; }
-extern "C" int64_t estk_xr_novelty_offset(void) { return kXrNovOff; }
 extern "C" int64_t estk_xr_workspace_bytes(int64_t n) { return n > 0 ? kXrDataOff + 2 * xr_image_bytes(n) : 0; }
 
 extern "C" int estk_rank_grad_xr_adam_h(estk_ctx* ctx, const float* returns, const float* novelty,
                                         float w_rew, float w_nov, int32_t P, int32_t world, int32_t rank,
                                         const uint16_t* table16, const int64_t* offsets, const int32_t* order,
                                         int32_t pair_begin, int32_t pairs_local, int64_t n,
-                                        void* const* peer_ws, int32_t gather, float* theta, float* m, float* v,
+                                        void* const* peer_ws, float* theta, float* m, float* v,
                                         estk_state* state, const estk_adam_desc* adam,
                                         int32_t* ranks_out, int32_t* ranks2_out, float* grad_out, void* stream) {
   ESTK_CHECK_ARG(table16 != nullptr, "estk_rank_grad_xr_adam_h: null table16");
-  ESTK_CHECK_ARG(!gather || (size_t)P * 8 <= 64 * 1024,
-                 "estk_rank_grad_xr_adam_h: gather needs population_size <= 8192 (keys in shared memory)");
   int rc = check_common(ctx, returns, P, table16, offsets, n, "estk_rank_grad_xr_adam_h");
   if (rc) return rc;
   ESTK_CHECK_ARG(world >= 2 && world <= ESTK_MAX_PEERS && rank >= 0 && rank < world,
@@ -824,14 +776,7 @@ extern "C" int estk_rank_grad_xr_adam_h(estk_ctx* ctx, const float* returns, con
   p.ranks_out = ranks_out; p.ranks2_out = ranks2_out;
   p.fused_adam = 1; p.grad_out = grad_out;
   p.theta = theta; p.m = m; p.v = v; p.state = state; p.adam = *adam;
-  p.xr = world; p.xr_rank = rank; p.xr_gather = gather ? 1 : 0;
-  if (gather) {
-    const unsigned char* own = static_cast<const unsigned char*>(peer_ws[rank]);
-    ESTK_CHECK_ARG(reinterpret_cast<const unsigned char*>(returns) == own + kXrRetOff &&
-                   (!novelty || reinterpret_cast<const unsigned char*>(novelty) == own + kXrNovOff),
-                   "estk_rank_grad_xr_adam_h: with gather, returns / novelty must be the arrays inside the caller's "
-                   "own workspace (estk_xr_returns_offset / estk_xr_novelty_offset)");
-  }
+  p.xr = world; p.xr_rank = rank;
   for (int q = 0; q < world; ++q) {
     ESTK_CHECK_ARG(peer_ws[q] && ESTK_ALIGNED16(peer_ws[q]), "estk_rank_grad_xr_adam_h: peer workspace %d null or unaligned", q);
     p.peer[q] = static_cast<unsigned char*>(peer_ws[q]);

@@ -628,23 +628,10 @@ class ES:
         return t_rm.view(self.n_workers, 2, self._pairs_local).permute(1, 0, 2).reshape(-1)
 
     def _rm_buffers(self):
-        """Rank-major returns / novelty ``[W][2][pairs/W]``.  With peer-memory workspaces they live INSIDE this
-        rank's workspace: the evaluate kernels write the own block there and the rank+gradient kernel reads the
-        other blocks from the peers' workspaces (no all-gather call); otherwise plain device buffers that an
-        in-place NCCL all-gather completes."""
         if getattr(self, "_returns_rm", None) is None:
-            peers = self._peer_workspaces()
-            self._rm_gather = (peers is not None and self.population_size <= 8192
-                               and os.environ.get("ESTORCH_B200_PEER_GATHER", "1") != "0")
-            if self._rm_gather:
-                r, nv = self._be.xr_returns_views(peers[self.rank], self.n_workers, self._pairs_local)
-                r.zero_(); nv.zero_()
-                self._returns_rm = r
-                self._novelty_rm = nv if self._ALGORITHM_TYPE == _Algorithm.novelty else None
-            else:
-                self._returns_rm = self._be.zeros(self.n_workers, 2, self._pairs_local)
-                self._novelty_rm = self._be.zeros(self.n_workers, 2, self._pairs_local) \
-                    if self._ALGORITHM_TYPE == _Algorithm.novelty else None
+            self._returns_rm = self._be.zeros(self.n_workers, 2, self._pairs_local)
+            self._novelty_rm = self._be.zeros(self.n_workers, 2, self._pairs_local) \
+                if self._ALGORITHM_TYPE == _Algorithm.novelty else None
         return self._returns_rm, self._novelty_rm
 
     def _all_gather_rm(self, t_rm):
@@ -824,13 +811,11 @@ class ES:
         else:
             peers = self._peer_workspaces() if rm else None
             if peers is not None:
-                # ONE launch: (all-gather of the returns,) ranks, partial gradient, sum over the GPUs through NVLink
-                # peer memory, Adam
-                if not self._rm_gather:
-                    self._all_gather_rm(R)
+                # ONE launch: ranks, partial gradient, sum over the GPUs through NVLink peer memory, Adam
+                self._all_gather_rm(R)
                 be.rank_grad_xr_adam(R.view(-1), None, 1.0, 0.0, P, W, self.rank, gt, self._offsets, self._order,
                                      pb, pl, peers, slot.theta, slot.m, slot.v, slot.state, ad, self._ranks, None,
-                                     self._grad, gather=self._rm_gather)
+                                     self._grad)
             else:
                 if rm:
                     self._all_gather_rm(R)
@@ -1361,12 +1346,11 @@ class NS_ES(ES):
         else:
             peers = self._peer_workspaces() if rm else None
             if peers is not None:
-                if not self._rm_gather:
-                    self._all_gather_rm(R)
-                    self._all_gather_rm(N)
+                self._all_gather_rm(R)
+                self._all_gather_rm(N)
                 be.rank_grad_xr_adam(R.view(-1), N.view(-1), w_rew, w_nov, P, W, self.rank, gt, self._offsets,
                                      self._order, pb, pl, peers, slot.theta, slot.m, slot.v, slot.state, ad,
-                                     self._ranks, self._ranks2, self._grad, gather=self._rm_gather)
+                                     self._ranks, self._ranks2, self._grad)
             else:
                 if rm:
                     self._all_gather_rm(R)

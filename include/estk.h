@@ -312,13 +312,6 @@ ESTK_API int estk_rank_grad_h(estk_ctx* ctx, const float* returns, const float* 
 #define ESTK_MAX_PEERS 16
 #define ESTK_PEER_HANDLE_BYTES 64
 ESTK_API int64_t estk_xr_workspace_bytes(int64_t n);
-/* With gather != 0 the all-gather of the returns happens in the same kernel too: `returns` (and `novelty`) must be
- * the rank-major arrays INSIDE the caller's own workspace, at estk_xr_returns_offset() / estk_xr_novelty_offset()
- * bytes from its base (ESTK_MAX_POPULATION floats each); on entry only the caller's own block
- * [rank][2][pairs/world] is valid (its evaluate kernels wrote it), the kernel reads the other blocks from the
- * peers' workspaces after a first flag barrier and completes the caller's copy.  population_size <= 8192. */
-ESTK_API int64_t estk_xr_returns_offset(void);
-ESTK_API int64_t estk_xr_novelty_offset(void);
 ESTK_API int estk_peer_alloc(estk_ctx* ctx, int64_t bytes, void** ptr_out, unsigned char* handle_out);
 ESTK_API int estk_peer_open(estk_ctx* ctx, const unsigned char* handle, void** ptr_out);
 ESTK_API int estk_peer_close(estk_ctx* ctx, void* ptr);
@@ -327,7 +320,7 @@ ESTK_API int estk_rank_grad_xr_adam_h(estk_ctx* ctx, const float* returns, const
                              float w_rew, float w_nov, int32_t P, int32_t world, int32_t rank,
                              const uint16_t* table16, const int64_t* offsets, const int32_t* order,
                              int32_t pair_begin, int32_t pairs_local, int64_t n,
-                             void* const* peer_ws, int32_t gather, float* theta, float* m, float* v,
+                             void* const* peer_ws, float* theta, float* m, float* v,
                              estk_state* state, const estk_adam_desc* adam,
                              int32_t* ranks_out, int32_t* ranks2_out, float* grad_out, void* stream);
 

@@ -40,22 +40,13 @@ try:
         peers = [mine[0] if r == rank else be.peer_open(handles[r]) for r in range(W)]
         ranks = be.alloc(P, dtype=torch.int32)
         bad = 0
-        Rws, _ = be.xr_returns_views(mine[0], W, pl)      # the returns array inside this rank's workspace (gather mode)
         A = [torch.zeros(n, device=be.device) for _ in range(3)]; sA = be.zeros(32, dtype=torch.uint8); gA = be.alloc(n)
         B = [torch.zeros(n, device=be.device) for _ in range(3)]; sB = be.zeros(32, dtype=torch.uint8); gB = be.alloc(n)
         for it in range(12):
             g = torch.Generator(device="cpu").manual_seed(100 + it)
             ret = torch.randn(P, generator=g).to(be.device)            # same returns on every rank, new every iteration
-            if it % 2 == 0:
-                be.rank_grad_xr_adam(ret, None, 1.0, 0.0, P, W, rank, tb16, offs, order, rank * pl, pl, peers,
-                                     A[0], A[1], A[2], sA, ad, ranks, None, gA)
-            else:       # the all-gather of the returns inside the kernel: only this rank's block is supplied
-                Rws.fill_(float("nan"))
-                Rws[rank].copy_(ret.view(W, 2, pl)[rank])
-                be.rank_grad_xr_adam(Rws.view(-1), None, 1.0, 0.0, P, W, rank, tb16, offs, order, rank * pl, pl, peers,
-                                     A[0], A[1], A[2], sA, ad, ranks, None, gA, gather=True)
-                torch.cuda.synchronize()
-                assert torch.equal(Rws.view(-1), ret), "gathered returns differ"
+            be.rank_grad_xr_adam(ret, None, 1.0, 0.0, P, W, rank, tb16, offs, order, rank * pl, pl, peers,
+                                 A[0], A[1], A[2], sA, ad, ranks, None, gA)
             be.rank_grad(ret, None, 1.0, 0.0, P, tb16, offs, order, rank * pl, pl, n, gB, ranks, None, world=W)
             dist.all_reduce(gB)
             graw = gB.clone()
@@ -73,16 +64,6 @@ try:
         ret = torch.randn(P, device=be.device)
         t_xr = timed(lambda: be.rank_grad_xr_adam(ret, None, 1.0, 0.0, P, W, rank, tb16, offs, order, rank * pl, pl, peers,
                                                   A[0], A[1], A[2], sA, ad, ranks, None, gA))
-        Rws.view(-1).copy_(ret)
-        t_xg = timed(lambda: be.rank_grad_xr_adam(Rws.view(-1), None, 1.0, 0.0, P, W, rank, tb16, offs, order, rank * pl, pl,
-                                                  peers, A[0], A[1], A[2], sA, ad, ranks, None, gA, gather=True))
-
-        def nccl_gather_path():
-            dist.all_gather_into_tensor(Rg.view(-1), Rg[rank].reshape(-1))
-            be.rank_grad_xr_adam(Rg.view(-1), None, 1.0, 0.0, P, W, rank, tb16, offs, order, rank * pl, pl, peers,
-                                 A[0], A[1], A[2], sA, ad, ranks, None, gA)
-        Rg = ret.clone().view(W, 2, pl)
-        t_ng = timed(nccl_gather_path)
         t_rg = timed(lambda: be.rank_grad(ret, None, 1.0, 0.0, P, tb16, offs, order, rank * pl, pl, n, gB, ranks, None, world=W))
 
         def nccl_path():
@@ -92,7 +73,6 @@ try:
         t_nc = timed(nccl_path)
         t_ar = timed(lambda: dist.all_reduce(gB))
         if rank == 0:
-            print(f"W={W} n={n}: with the returns all-gather: in the kernel {t_xg:.1f} | NCCL all-gather + kernel {t_ng:.1f}", flush=True)
             print(f"W={W} n={n}: rank+gradient+NVLink sum+Adam {t_xr:.1f} | rank+partial gradient alone {t_rg:.1f} | "
                   f"rank+partial, NCCL all-reduce, clamp+Adam {t_nc:.1f} | NCCL all-reduce alone {t_ar:.1f}  (us, max over ranks)",
                   flush=True)
