@@ -87,10 +87,17 @@ def _release_shm(shm, owner):
 _LIVE = weakref.WeakSet()      # instances that may hold CUDA graphs with captured collectives
 
 
+_OWN_PROCESS_GROUP = False     # this module called init_process_group (then it also destroys it at exit)
+_EXIT_HOOK = False
+
+
 def _shutdown_dist():
-    """Process exit of a launcher-started rank.  A CUDA graph that captured NCCL kernels keeps a
-    reference on the communicator, and destroying the communicator first never returns
-    (profiles/r02_launcher_check.log, first run): graphs go first, then the process group."""
+    """Process exit of a multi-GPU rank.  A CUDA graph that captured NCCL kernels keeps a reference on
+    the communicator, and destroying the communicator first never returns
+    (profiles/r02_launcher_check.log, first run): graphs go first, then the peer-memory workspaces
+    (every rank unmaps, barrier, every rank frees), then -- if this module created it -- the process
+    group.  A script that destroys the process group itself calls ``es.close()`` (or drops the
+    instance) first."""
     import gc
     import torch.distributed as dist
     for es in list(_LIVE):
@@ -99,14 +106,15 @@ def _shutdown_dist():
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     backends = [es._be for es in list(_LIVE) if hasattr(es._be, "peer_close_all")]
-    for be in backends:                   # peer-memory workspaces: every rank unmaps, then every rank frees
+    for be in backends:
         be.peer_close_all()
     if dist.is_initialized():
         if backends:
             dist.barrier()
         for be in backends:
             be.peer_free_all()
-        dist.destroy_process_group()
+        if _OWN_PROCESS_GROUP:
+            dist.destroy_process_group()
 
 
 _NVTX = os.environ.get("ESTORCH_B200_NVTX", "0") == "1"
@@ -653,6 +661,8 @@ class ES:
         #  all-reduce: measured 51 vs 50 us at n = 214 k, 60 vs 45 us at n = 6 k, 212 vs 233 us at n = 1 M on 2 GPUs)
         ok = (self._dev.type == "cuda" and hasattr(be, "peer_alloc") and 2 <= W <= 16 and mode != "0"
               and (self.n_parameters >= (1 << 18) or mode == "force"))
+        if not ok:            # decided by the job's configuration alone: the same on every rank, no collective
+            return None
         mine = err = None
         if ok:
             try:
@@ -680,12 +690,28 @@ class ES:
     def _ensure_dist(self):
         if self.n_workers > 1:
             import torch.distributed as dist
+            global _OWN_PROCESS_GROUP, _EXIT_HOOK
             _LIVE.add(self)
             if not dist.is_initialized():
                 backend = "nccl" if self._dev.type == "cuda" else "gloo"
                 dist.init_process_group(backend=backend)
+                _OWN_PROCESS_GROUP = True
+            if not _EXIT_HOOK:
                 import atexit
                 atexit.register(_shutdown_dist)
+                _EXIT_HOOK = True
+
+    def close(self):
+        """Release what must go before ``torch.distributed.destroy_process_group()``: the CUDA graphs of the
+        fused generation (they pin the NCCL communicator) and this process's mappings of the other ranks'
+        peer-memory workspaces.  Call it on EVERY rank (it switches the gradient sum back to NCCL, which all
+        ranks must agree on); training can continue afterwards (graphs are re-captured)."""
+        self.__dict__.pop("_graphs", None)
+        if self._dev.type == "cuda":
+            torch.cuda.synchronize(self._dev)
+        if hasattr(self._be, "peer_close_all") and self.__dict__.get("_peer_ptrs") is not None:
+            self._be.peer_close_all()
+            self._peer_ptrs = None
 
     # ------------------------------------------------------------------ fused generation
     def _adam_desc(self, optimizer):
