@@ -589,11 +589,12 @@ int launch_rank_grad(estk_ctx* ctx, RankGradParams& p, cudaStream_t stream) {
   constexpr int kThreads = T;
   int occ = 0;
   constexpr size_t kKeyBytesMax = 64 * 1024;             // P <= 8192 (BASELINE config 3); larger: global-memory path
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};                         // per device: one process may drive several GPUs
+  const int dev = ctx->device & 63;
+  if (!attr_set[dev]) {
     ESTK_CUDA(cudaFuncSetAttribute(rank_grad_kernel<NC, T, LOADS, T16, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kKeyBytesMax));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const size_t key_bytes = (size_t)p.P * 8 <= kKeyBytesMax ? (size_t)p.P * 8 : 0;
   p.keys_in_smem = key_bytes ? 1 : 0;
