@@ -613,6 +613,12 @@ class ES:
         that all ranks perturb the same centre and apply the same update."""
         if self.n_workers == 1:
             return
+        # Fused mode keeps the replicas bit-identical by construction (same returns, same sum order, same Adam
+        # bits on every rank), so a second train() call has nothing to broadcast: 20 MB + a pickled dict per
+        # call was 3 % of a 20-generation run on 8 GPUs.  Hooks mode (host agents may be stochastic per rank)
+        # and anything that rewrites the state (load_state_dict, sync_replicas()) synchronise again.
+        if self._fused and getattr(self, "_replicas_synced", False):
+            return
         import torch.distributed as dist
         for s_ in self._slots:
             s_.push_theta()
@@ -628,6 +634,17 @@ class ES:
         for k, v in box[0].items():
             setattr(self, k, v)
         self._host_cache = {}
+        self._replicas_synced = True
+
+    def sync_replicas(self):
+        """Make rank 0's parameters / optimizer state / algorithm state authoritative on every rank again (a
+        collective: call it on every rank).  Needed only after rank 0's policy was modified by hand between two
+        ``train()`` calls of a multi-GPU job; ``load_state_dict`` does it implicitly."""
+        self._replicas_synced = False
+        self._ensure_dist()
+        for s_ in self._slots:
+            s_.ensure_flat()
+        self._sync_replicas()
 
     # -- rank-major returns: every rank's evaluate kernel writes its (+, -) halves straight into its
     #    block of a [W, 2, pairs/W] buffer, ONE in-place all-gather completes it, and the rank kernel
@@ -1186,6 +1203,7 @@ class ES:
         if sd["noise_seed"] != self._noise_seed or sd["noise_table_size"] != self._table.numel():
             raise ValueError("checkpoint was written with a different noise table (seed or size)")
         self.sigma = sd["sigma"]
+        self._replicas_synced = False
         self._generation = int(sd["generation"])
         for s_, rec in zip(self._slots, sd["slots"]):
             s_.ensure_flat()

@@ -29,6 +29,26 @@ def main():
                  returns=es.population_returns, world=es.n_workers, pairs_local=es._pairs_local,
                  pair_begin=es._pair_begin, episode=es.episode_reward, best_reward=es.best_reward)
         return
+    if algo in ("es_two_calls", "es_one_call"):
+        # two consecutive train() calls of a multi-rank job (the second one does not broadcast the replicas again)
+        # must leave what one call of the same length leaves
+        dims = [4, 16, 2]
+        gg = torch.Generator().manual_seed(5)
+        obs, tgt = torch.randn(32, 4, generator=gg), torch.randn(32, 2, generator=gg)
+        torch.manual_seed(100 + int(os.environ["RANK"]))      # different construction-time policies per rank
+        es = E.ES(MLP, E.DeviceAgent, torch.optim.Adam, population_size=16, sigma=0.05, policy_kwargs={"dims": dims},
+                  agent_kwargs=dict(obs=obs, target=tgt), optimizer_kwargs={"lr": 0.01}, noise_table_size=1 << 12,
+                  noise_seed=3, _backend=OracleBackend())
+        es.log = lambda: None
+        if algo == "es_two_calls":
+            es.train(n_steps=3)
+            es.train(n_steps=2)
+        else:
+            es.train(n_steps=5)
+        np.savez(os.path.join(out_dir, f"rank{es.rank}.npz"), theta=es._slots[0].theta.numpy(),
+                 m=es._slots[0].m.numpy(), step=es.step, returns=es.population_returns,
+                 episode=float(es.episode_reward), best=float(es.best_reward), synced=bool(es._replicas_synced))
+        return
     if algo == "es_p8192":
         # BASELINE config 3's population (8192 members = 4096 antithetic pairs) sharded over the ranks, small policy
         dims = [4, 16, 2]

@@ -90,6 +90,19 @@ def test_world2_replicas_agree_without_preloaded_parameters(tmp_path, algo):
         assert float(r0["episode"]) == float(r1["episode"])
 
 
+def test_world2_two_train_calls_equal_one(tmp_path):
+    """A second train() call of a multi-rank fused job skips the replica broadcast (the replicas are bit-identical
+    by construction): 3 + 2 generations leave exactly what 5 leave, on both ranks."""
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    a0, a1 = _run(2, "es_two_calls", tmp_path / "a")
+    b0, b1 = _run(2, "es_one_call", tmp_path / "b")
+    assert bool(a0["synced"]) and bool(a1["synced"])
+    for k in ("theta", "m", "returns"):
+        np.testing.assert_array_equal(a0[k], a1[k])
+        np.testing.assert_array_equal(a0[k], b0[k])
+    assert float(a0["episode"]) == float(b0["episode"]) and float(a0["best"]) == float(b0["best"])
+
+
 def test_world2_population_8192_sharded(tmp_path):
     """BASELINE config 3's population size (8192 members, sigma 0.02) sharded over two ranks: 2048 pairs per
     rank, rank-major all-gather of the returns, every rank ranks all 8192, bit-identical replicas, and the
