@@ -94,9 +94,8 @@ _EXIT_HOOK = False
 def _shutdown_dist():
     """Process exit of a multi-GPU rank.  A CUDA graph that captured NCCL kernels keeps a reference on
     the communicator, and destroying the communicator first never returns
-    (profiles/r02_launcher_check.log, first run): graphs go first, then the peer-memory workspaces
-    (every rank unmaps, barrier, every rank frees), then -- if this module created it -- the process
-    group.  A script that destroys the process group itself calls ``es.close()`` (or drops the
+    (profiles/r02_launcher_check.log, first run): graphs go first, then the mappings of the peers'
+    workspaces, then -- if this module created it -- the process group.  A script that destroys the process group itself calls ``es.close()`` (or drops the
     instance) first."""
     import gc
     import torch.distributed as dist
@@ -105,16 +104,11 @@ def _shutdown_dist():
     gc.collect()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
-    backends = [es._be for es in list(_LIVE) if hasattr(es._be, "peer_close_all")]
-    for be in backends:
-        be.peer_close_all()
-    if dist.is_initialized():
-        if backends:
-            dist.barrier()
-        for be in backends:
-            be.peer_free_all()
-        if _OWN_PROCESS_GROUP:
-            dist.destroy_process_group()
+    for es in list(_LIVE):                # unmap the peers' workspaces; this process's own allocations are left to
+        if hasattr(es._be, "peer_close_all"):   # process teardown (freeing them needs every peer to have unmapped
+            es._be.peer_close_all()             # first, and a barrier in an exit hook would hang if a rank died)
+    if dist.is_initialized() and _OWN_PROCESS_GROUP:
+        dist.destroy_process_group()
 
 
 _NVTX = os.environ.get("ESTORCH_B200_NVTX", "0") == "1"
